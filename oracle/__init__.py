@@ -1,0 +1,153 @@
+"""ctypes front-end of the CPU oracle (oracle/cdf_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Importers allowed: tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl reference legs.
+The product package (cdftools_b200) must never import this module; tests/test_no_oracle_in_product.py checks.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_DIR = Path(__file__).resolve().parent
+_LIB = None
+
+EOS80, TEOS10, NEUTRAL = 0, 1, 2
+
+
+def build(force: bool = False) -> Path:
+    so = _DIR / "libcdforacle.so"
+    src = _DIR / "cdf_oracle.c"
+    hdr = _DIR.parent / "include" / "cdf_eos_coeffs.h"
+    if force or not so.exists() or so.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime):
+        subprocess.run(["make", "-C", str(_DIR), "-B", "libcdforacle.so"], check=True, capture_output=True)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = _DIR / "libcdforacle.so"
+        if not so.exists():
+            build()
+        _LIB = C.CDLL(str(so))
+        _LIB.oracle_eos_dlr.restype = C.c_double
+        _LIB.oracle_eos_dlr.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int]
+        _LIB.oracle_num_threads.restype = C.c_int
+    return _LIB
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def num_threads() -> int:
+    return int(lib().oracle_num_threads())
+
+
+def eos_dlr(t, s, depth, teos10=False) -> float:
+    return float(lib().oracle_eos_dlr(float(t), float(s), float(depth), int(teos10)))
+
+
+def sigmai_dep(t, s, pref, teos10=False):
+    t, s = _f32(t), _f32(s)
+    out = np.empty(t.shape, np.float64)
+    lib().oracle_sigmai_dep(C.c_size_t(t.size), _p(t, C.c_float), _p(s, C.c_float), C.c_float(pref), int(teos10),
+                            _p(out, C.c_double))
+    return out
+
+
+def sigmantr(t, s):
+    t, s = _f32(t), _f32(s)
+    out = np.empty(t.shape, np.float64)
+    lib().oracle_sigmantr(C.c_size_t(t.size), _p(t, C.c_float), _p(s, C.c_float), _p(out, C.c_double))
+    return out
+
+
+def basin_masks(vmask1, atl=None, ind=None, pac=None, zero_edges=True):
+    vmask1 = _f32(vmask1)
+    ny, nx = vmask1.shape
+    nb = 5 if atl is not None else 1
+    out = np.zeros((ny, nx, nb), np.int16)
+    a, i, p = (_f32(x) if x is not None else None for x in (atl, ind, pac))
+    lib().oracle_basin_masks(nx, ny, nb, _p(vmask1, C.c_float), _p(a, C.c_float), _p(i, C.c_float), _p(p, C.c_float),
+                             int(zero_edges), _p(out, C.c_int16))
+    return out
+
+
+def mask_e3v(e3v_file, vmask):
+    e, v = _f32(e3v_file), _f32(vmask)
+    out = np.empty(e.shape, np.float32)
+    lib().oracle_mask_e3v(C.c_size_t(e.size), _p(e, C.c_float), _p(v, C.c_float), _p(out, C.c_float))
+    return out
+
+
+def cdfmoc_record(e1v, e3m, ibmask, zv):
+    """-> dmoc (nz, ny, nb) float64, scanned (Sv).  cdfmoc.f90:352-388."""
+    e1v, e3m, zv = _f32(e1v), _f32(e3m), _f32(zv)
+    ibmask = np.ascontiguousarray(ibmask, np.int16)
+    nz, ny, nx = e3m.shape
+    nb = ibmask.shape[2]
+    assert zv.shape == (nz - 1, ny, nx) and e1v.shape == (ny, nx) and ibmask.shape[:2] == (ny, nx)
+    out = np.empty((nz, ny, nb), np.float64)
+    lib().oracle_cdfmoc_record(nx, ny, nz, nb, _p(e1v, C.c_float), _p(e3m, C.c_float), _p(ibmask, C.c_int16),
+                               _p(zv, C.c_float), _p(out, C.c_double))
+    return out
+
+
+def cdfmoc_output(dmoc):
+    nz, ny, nb = dmoc.shape
+    nv = nb + (1 if nb >= 5 else 0)
+    out = np.empty((nv, nz, ny), np.float32)
+    d = np.ascontiguousarray(dmoc, np.float64)
+    lib().oracle_cdfmoc_output(ny, nz, nb, _p(d, C.c_double), _p(out, C.c_float))
+    return out
+
+
+def sigma_axis(nbins, sigmin, sigstp):
+    out = np.empty(nbins, np.float32)
+    lib().oracle_sigma_axis(int(nbins), C.c_float(sigmin), C.c_float(sigstp), _p(out, C.c_float))
+    return out
+
+
+def default_bins(pref, lntr=False):
+    nb, smin, sstp = C.c_int(), C.c_float(), C.c_float()
+    rc = lib().oracle_default_bins(C.c_float(pref), int(lntr), C.byref(nb), C.byref(smin), C.byref(sstp))
+    if rc:
+        raise SystemExit(rc)
+    return nb.value, smin.value, sstp.value
+
+
+def cdfmocsig_record(e1v, e3v, ibmask, zv, zt, zs, spv, spt, sps, pref, eos, sigmin, sigstp, nbins, zveiv=None,
+                     faithful=False, want_bins=True):
+    """-> (dmoc (ny, nbins, nb) float64 scanned, ibin (nz-1, ny, nx) int32 or None).  cdfmocsig.f90:366-475."""
+    e1v, e3v, zv, zt, zs = (_f32(x) for x in (e1v, e3v, zv, zt, zs))
+    ibmask = np.ascontiguousarray(ibmask, np.int16)
+    nzm1, ny, nx = zv.shape
+    nz = nzm1 + 1
+    nb = ibmask.shape[2]
+    assert e3v.shape[0] >= nzm1 and e3v.shape[1:] == (ny, nx)
+    ze = _f32(zveiv) if zveiv is not None else None
+    out = np.empty((ny, nbins, nb), np.float64)
+    bins = np.empty((nzm1, ny, nx), np.int32) if want_bins else None
+    lib().oracle_cdfmocsig_record(nx, ny, nz, nb, int(nbins), C.c_float(sigmin), C.c_float(sigstp), C.c_float(pref),
+                                  int(eos), _p(e1v, C.c_float), _p(e3v, C.c_float), _p(ibmask, C.c_int16),
+                                  C.c_float(spv), C.c_float(spt), C.c_float(sps), _p(zv, C.c_float),
+                                  _p(zt, C.c_float), _p(zs, C.c_float), _p(ze, C.c_float), int(faithful),
+                                  _p(out, C.c_double), _p(bins, C.c_int32))
+    return out, bins
+
+
+def cdfmocsig_output(dmoc):
+    ny, nbins, nb = dmoc.shape
+    out = np.empty((nb, nbins, ny), np.float32)
+    d = np.ascontiguousarray(dmoc, np.float64)
+    lib().oracle_cdfmocsig_output(ny, nb, nbins, _p(d, C.c_double), _p(out, C.c_float))
+    return out

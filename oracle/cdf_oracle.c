@@ -1,0 +1,382 @@
+/*
+ * cdf_oracle.c -- CPU restatement of the cdfmoc / cdfmocsig hot path of meom-group/CDFTOOLS.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it.  The product path
+ * (cdftools_b200/csrc + libcdfgpu.so) never calls anything in this file and has no CPU fallback.
+ *
+ * Pinning status: the reference carries no golden vectors or tests for the zonal integral,
+ * the scan, the binning or the scatter and no Fortran compiler or
+ * NetCDF library exists in this image, so the reference itself cannot be run here:
+ *   - EOS routines (sigmai_dep, sigmantr): PINNED by the three check values printed in the
+ *     reference's comments (src/eos.f90:646,817,820) -- see tests/test_oracle_eos.py.
+ *   - zonal integral / scan / binning / scatter: PARITY UNPINNED by the reference; pinned only by
+ *     (i) an independent NumPy restatement agreeing bit for bit (oracle/np_oracle.py),
+ *     (ii) a hand-computed 4x3x3 case, (iii) algebraic property tests.
+ *
+ * Arithmetic rules: REAL(4) temporaries are `float`, REAL(8) are `double`,
+ * products associate left to right exactly as written in the Fortran, sums run sequentially in the
+ * reference loop order, no FMA contraction (compile with -ffp-contract=off, no -ffast-math).
+ *
+ * Memory layout: Fortran column-major arrays are passed flat, first index fastest:
+ *   e1v(nx,ny)        -> e1v[j*nx+i]
+ *   e3v(nx,ny,nz)     -> e3v[(k*ny+j)*nx+i]
+ *   ibmask(nb,nx,ny)  -> ibmask[(j*nx+i)*nb+b]          (INTEGER(2), basin fastest)
+ *   dmoc(nb,ny,nz)    -> dmoc[(k*ny+j)*nb+b]            (cdfmoc.f90:287)
+ *   dmoc(nb,nbins,ny) -> dmoc[(j*nbins+bin)*nb+b]       (cdfmocsig.f90:313)
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/cdf_eos_coeffs.h"
+
+#define CDF_EOS_EOS80 0
+#define CDF_EOS_TEOS10 1
+#define CDF_EOS_NEUTRAL 2
+
+int oracle_abi_version(void) { return 1; }
+
+int oracle_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * a1. basin mask assembly -- src/cdfmoc.f90:325-336 (cdfmocsig.f90:347-359).
+ * getvar() returns REAL(4); assignment to INTEGER(2) truncates toward zero.
+ * Order: 1 global(vmask k=1), 2 atl, 3 indo-pacific = min(1, pac+ind), 4 ind, 5 pac.
+ * The i=1 and i=nx columns of the GLOBAL mask are zeroed (periodic overlap).
+ * In cdfmocsig the zeroing sits inside IF(lbas) (:356-358): `zero_edges_always`=0 reproduces that.
+ * ------------------------------------------------------------------------------------------- */
+void oracle_basin_masks(int nx, int ny, int nb, const float *vmask1, const float *atl, const float *ind,
+                        const float *pac, int zero_edges, int16_t *ibmask)
+{
+    for (int j = 0; j < ny; ++j)
+        for (int i = 0; i < nx; ++i) {
+            size_t c = (size_t)j * nx + i;
+            int16_t *m = ibmask + c * nb;
+            m[0] = (int16_t)vmask1[c];
+            if (nb >= 5) {
+                m[1] = (int16_t)atl[c];
+                m[3] = (int16_t)ind[c];
+                m[4] = (int16_t)pac[c];
+                m[2] = (int16_t)(m[4] + m[3]);
+                if (m[2] > 0) m[2] = 1;
+            }
+        }
+    if (zero_edges)
+        for (int j = 0; j < ny; ++j) {
+            ibmask[((size_t)j * nx + 0) * nb] = 0;
+            ibmask[((size_t)j * nx + (nx - 1)) * nb] = 0;
+        }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * a2. get_e3v -- src/cdfmoc.f90:590-594: e3v(:,:) = e3v_file(:,:) * ivmask(:,:)
+ * ivmask is INTEGER(2) (truncated from the REAL(4) getvar result); product is REAL(4).
+ * ------------------------------------------------------------------------------------------- */
+void oracle_mask_e3v(size_t n, const float *e3v_file, const float *vmask, float *e3m)
+{
+    for (size_t c = 0; c < n; ++c) {
+        int16_t iv = (int16_t)vmask[c];
+        e3m[c] = e3v_file[c] * (float)iv;
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * a3 + a4. cdfmoc record -- src/cdfmoc.f90:352-388.
+ *   dmoc(b,j,k) = dmoc(b,j,k) - e1v(i,j)*e3v(i,j,k)*ibmask(b,i,j)*zv(i,j)*1.d0     (:373-374)
+ * The REAL(4)*REAL(4)*INTEGER(2)*REAL(4) chain is evaluated left to right in REAL(4); *1.d0 widens.
+ * zv holds levels 1..nz-1 only (level nz is never read, :355).  No missing-value scrub (:357).
+ *   dmoc(:,j,k) = dmoc(:,j,k+1) + dmoc(:,j,k)/1.d6, k = nz-1..1                      (:385)
+ * ------------------------------------------------------------------------------------------- */
+void oracle_cdfmoc_record(int nx, int ny, int nz, int nb, const float *e1v, const float *e3m,
+                          const int16_t *ibmask, const float *zv, double *dmoc)
+{
+    memset(dmoc, 0, sizeof(double) * (size_t)nb * ny * nz);
+    for (int k = 0; k < nz - 1; ++k)
+        for (int b = 0; b < nb; ++b) {
+#pragma omp parallel for schedule(runtime)
+            for (int j = 0; j < ny; ++j) {
+                double acc = dmoc[((size_t)k * ny + j) * nb + b];
+                const float *pe1 = e1v + (size_t)j * nx;
+                const float *pe3 = e3m + ((size_t)k * ny + j) * nx;
+                const float *pv = zv + ((size_t)k * ny + j) * nx;
+                const int16_t *pm = ibmask + (size_t)j * nx * nb + b;
+                for (int i = 0; i < nx; ++i) {
+                    float t = pe1[i] * pe3[i];
+                    t = t * (float)pm[(size_t)i * nb];
+                    t = t * pv[i];
+                    acc = acc - (double)t;
+                }
+                dmoc[((size_t)k * ny + j) * nb + b] = acc;
+            }
+        }
+#pragma omp parallel for schedule(runtime)
+    for (int j = 0; j < ny; ++j)
+        for (int k = nz - 2; k >= 0; --k)
+            for (int b = 0; b < nb; ++b) {
+                size_t o = ((size_t)k * ny + j) * nb + b;
+                size_t o1 = ((size_t)(k + 1) * ny + j) * nb + b;
+                dmoc[o] = dmoc[o1] + dmoc[o] / 1.0e6;
+            }
+}
+
+/* a5. output conversion -- src/cdfmoc.f90:520-551.  out has (nb + (nb>=5)) variables of (nz,ny) REAL(4):
+ * out[v][k][j] = REAL(dmoc(v,j,k)); last variable inp0 = REAL(dmoc(glo)-dmoc(atl)) (:549). */
+void oracle_cdfmoc_output(int ny, int nz, int nb, const double *dmoc, float *out)
+{
+    for (int b = 0; b < nb; ++b)
+        for (int k = 0; k < nz; ++k)
+            for (int j = 0; j < ny; ++j)
+                out[((size_t)b * nz + k) * ny + j] = (float)dmoc[((size_t)k * ny + j) * nb + b];
+    if (nb >= 5)
+        for (int k = 0; k < nz; ++k)
+            for (int j = 0; j < ny; ++j) {
+                size_t o = ((size_t)k * ny + j) * nb;
+                out[((size_t)nb * nz + k) * ny + j] = (float)(dmoc[o + 0] - dmoc[o + 1]);
+            }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * a8. sigmai_dep -- src/eos.f90:842-882 (coefficients: eos_init :207-279 / :408-466).
+ * `teos10` selects the coefficient set.  pref is REAL(4) widened before dlh = pref*r1_Z0.
+ * eos_dlr() is the four nested Horner polynomials and their combination (:858-879), parenthesised
+ * exactly as the reference writes them.
+ * ------------------------------------------------------------------------------------------- */
+static inline double eos_dlr(const double *C, double dlt, double dls, double dlh)
+{
+#define E(i, j, k) C[I_EOS##i##j##k]
+    double dlr3 = E(0, 1, 3) * dlt + E(1, 0, 3) * dls + E(0, 0, 3);
+    double dlr2 = (E(0, 2, 2) * dlt + E(1, 1, 2) * dls + E(0, 1, 2)) * dlt + (E(2, 0, 2) * dls + E(1, 0, 2)) * dls +
+                  E(0, 0, 2);
+    double dlr1 = (((E(0, 4, 1) * dlt + E(1, 3, 1) * dls + E(0, 3, 1)) * dlt + (E(2, 2, 1) * dls + E(1, 2, 1)) * dls +
+                    E(0, 2, 1)) * dlt +
+                   ((E(3, 1, 1) * dls + E(2, 1, 1)) * dls + E(1, 1, 1)) * dls + E(0, 1, 1)) * dlt +
+                  (((E(4, 0, 1) * dls + E(3, 0, 1)) * dls + E(2, 0, 1)) * dls + E(1, 0, 1)) * dls + E(0, 0, 1);
+    double dlr0 =
+        (((((E(0, 6, 0) * dlt + E(1, 5, 0) * dls + E(0, 5, 0)) * dlt + (E(2, 4, 0) * dls + E(1, 4, 0)) * dls +
+            E(0, 4, 0)) * dlt +
+           ((E(3, 3, 0) * dls + E(2, 3, 0)) * dls + E(1, 3, 0)) * dls + E(0, 3, 0)) * dlt +
+          (((E(4, 2, 0) * dls + E(3, 2, 0)) * dls + E(2, 2, 0)) * dls + E(1, 2, 0)) * dls + E(0, 2, 0)) * dlt +
+         ((((E(5, 1, 0) * dls + E(4, 1, 0)) * dls + E(3, 1, 0)) * dls + E(2, 1, 0)) * dls + E(1, 1, 0)) * dls +
+         E(0, 1, 0)) * dlt +
+        (((((E(6, 0, 0) * dls + E(5, 0, 0)) * dls + E(4, 0, 0)) * dls + E(3, 0, 0)) * dls + E(2, 0, 0)) * dls +
+         E(1, 0, 0)) * dls +
+        E(0, 0, 0);
+#undef E
+    return ((dlr3 * dlh + dlr2) * dlh + dlr1) * dlh + dlr0;
+}
+
+void oracle_sigmai_dep(size_t n, const float *ptem, const float *psal, float pref, int teos10, double *out)
+{
+    const double *C = teos10 ? CDF_TEOS10_COEF : CDF_EOS80_COEF;
+    const double rdeltaS = teos10 ? CDF_TEOS10_RDELTAS : CDF_EOS80_RDELTAS;
+    const double r1_S0 = teos10 ? CDF_TEOS10_R1_S0 : CDF_EOS80_R1_S0;
+    const double r1_T0 = 1.0 / 40.0;
+    const double r1_Z0 = 1.e-4;
+    const double rau0 = 1000.0;
+    const double *R = CDF_EOS_R0;
+    double dlh = (double)pref * r1_Z0;
+    double dlref = (((((R[5] * dlh + R[4]) * dlh + R[3]) * dlh + R[2]) * dlh + R[1]) * dlh + R[0]) * dlh;
+#pragma omp parallel for schedule(static)
+    for (size_t c = 0; c < n; ++c) {
+        double dlt = (double)ptem[c] * r1_T0;
+        double dls = sqrt(fabs((double)psal[c] + rdeltaS) * r1_S0);
+        double dltm = (psal[c] == 0.0f) ? 0.0 : 1.0;
+        double dlr = eos_dlr(C, dlt, dls, dlh);
+        out[c] = (dlr + dlref - rau0) * dltm;
+    }
+}
+
+/* dlr alone: the quantity the reference's comment check values are quoted on (eos.f90:817,820 vs :879). */
+double oracle_eos_dlr(float t, float s, float depth, int teos10)
+{
+    const double *C = teos10 ? CDF_TEOS10_COEF : CDF_EOS80_COEF;
+    const double rdeltaS = teos10 ? CDF_TEOS10_RDELTAS : CDF_EOS80_RDELTAS;
+    const double r1_S0 = teos10 ? CDF_TEOS10_R1_S0 : CDF_EOS80_R1_S0;
+    double dlt = (double)t * (1.0 / 40.0);
+    double dls = sqrt(fabs((double)s + rdeltaS) * r1_S0);
+    return eos_dlr(C, dlt, dls, (double)depth * 1.e-4);
+}
+
+/* sigmantr -- src/eos.f90:661-684 (McDougall & Jackett 2005 neutral density, minus 1000). */
+void oracle_sigmantr(size_t n, const float *ptem, const float *psal, double *out)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t c = 0; c < n; ++c) {
+        double dl_t = ptem[c];
+        double dl_s = psal[c];
+        double dl_sr = sqrt(fabs(dl_s));
+        double dl_r1 = ((-4.3159255086706703e-4 * dl_t + 8.1157118782170051e-2) * dl_t + 2.2280832068441331e-1) * dl_t +
+                       1002.3063688892480e0;
+        double dl_r2 = (-1.7052298331414675e-7 * dl_s - 3.1710675488863952e-3 * dl_t - 1.0304537539692924e-4) * dl_s;
+        double dl_r3 = (((-2.3850178558212048e-9 * dl_t - 1.6212552470310961e-7) * dl_t + 7.8717799560577725e-5) * dl_t +
+                        4.3907692647825900e-5) * dl_t + 1.0e0;
+        double dl_r4 = ((-2.2744455733317707e-9 * dl_t * dl_t + 6.0399864718597388e-6) * dl_t - 5.1268124398160734e-4) * dl_s;
+        double dl_r5 = (-1.3409379420216683e-9 * dl_t * dl_t - 3.6138532339703262e-5) * dl_s * dl_sr;
+        out[c] = (dl_r1 + dl_r2) / (dl_r3 + dl_r4 + dl_r5) - 1000.e0;
+    }
+}
+
+/* a12. bin axis -- src/cdfmocsig.f90:302-304: sigma(ji) = sigmin + (ji-0.5)*sigstp, all REAL(4). */
+void oracle_sigma_axis(int nbins, float sigmin, float sigstp, float *sigma)
+{
+    for (int n = 1; n <= nbins; ++n) {
+        float t = (float)n - 0.5f;
+        t = t * sigstp;
+        sigma[n - 1] = sigmin + t;
+    }
+}
+
+/* a12. default bins by INT(pref) -- src/cdfmocsig.f90:265-292.  returns 0 ok, 99 = STOP 99. */
+int oracle_default_bins(float pref, int lntr, int *nbins, float *sigmin, float *sigstp)
+{
+    if (lntr) { *nbins = 52; *sigmin = 1023.f; *sigstp = 0.1f; return 0; }
+    switch ((int)pref) {
+    case 0: *nbins = 52; *sigmin = 23.f; *sigstp = 0.1f; return 0;
+    case 1000: *nbins = 88; *sigmin = 24.f; *sigstp = 0.1f; return 0;
+    case 2000: *nbins = 158; *sigmin = 30.f; *sigstp = 0.05f; return 0;
+    default: return 99;
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * a6..a9 for one level: scrub, area, itmask, density, bin -- src/cdfmocsig.f90:374-403.
+ * zv/zt/zs are scrubbed IN PLACE (as the WHERE statements do); zarea, ibin are outputs.
+ * eos: 0 EOS80, 1 TEOS10, 2 neutral (-ntr).
+ * ------------------------------------------------------------------------------------------- */
+void oracle_mocsig_level_prep(int nx, int ny, float *zv, float *zt, float *zs, const float *zveiv, const float *e1v,
+                              const float *e3v, float zspv, float zspt, float zsps, float pref, int eos, float sigmin,
+                              float sigstp, int nbins, float *zarea, int16_t *itmask, int32_t *ibin, double *dens)
+{
+    size_t n = (size_t)nx * ny;
+    for (size_t c = 0; c < n; ++c)
+        if (zv[c] == zspv) zv[c] = 0.f; /* :375 */
+    if (zveiv)
+        for (size_t c = 0; c < n; ++c) zv[c] = zv[c] + zveiv[c]; /* :378 */
+    for (size_t c = 0; c < n; ++c)
+        if (zt[c] == zspt) zt[c] = 0.f; /* :383 */
+    for (size_t c = 0; c < n; ++c)
+        if (zs[c] == zsps) zs[c] = 0.f; /* :384 */
+    for (size_t c = 0; c < n; ++c) zarea[c] = e1v[c] * e3v[c]; /* :390, e3v NOT vmask-masked */
+    for (size_t c = 0; c < n; ++c) itmask[c] = (zs[c] == zsps) ? 0 : 1; /* :393-394 (after the scrub) */
+    if (eos == CDF_EOS_NEUTRAL)
+        oracle_sigmantr(n, zt, zs, dens); /* :395 */
+    else
+        oracle_sigmai_dep(n, zt, zs, pref, eos == CDF_EOS_TEOS10, dens); /* :396 */
+    for (size_t c = 0; c < n; ++c) {
+        float zttmp = (float)(dens[c] * (double)itmask[c]); /* :399 */
+        float q = (zttmp - sigmin) / sigstp;                 /* :401 REAL(4) */
+        int32_t ib = (int32_t)q;                             /* INT() truncates toward zero */
+        if (ib < 1) ib = 1;                                  /* :402 */
+        if (ib > nbins) ib = nbins;                          /* :403 */
+        ibin[c] = ib;
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * a10 faithful: src/cdfmocsig.f90:405-442 -- dmoc_tmp(nbins,nx) zeroed per row, scatter, then the
+ * DENSE (basin, bin, i) accumulation with dmoc_tmp*ibmask in REAL(8).
+ * a10 direct: the same sums without the dense pass (adds only the non-zero entry of each column).
+ * Adding +0.0 to an accumulator that started at +0.0 never changes it, so both forms are bit-identical
+ * for finite inputs; the direct form is what an O(cells) CPU code would do and is the fair baseline.
+ * ------------------------------------------------------------------------------------------- */
+void oracle_mocsig_level_accum(int nx, int ny, int nb, int nbins, const float *zv, const float *zarea,
+                               const int32_t *ibin, const int16_t *ibmask, int faithful, double *dmoc)
+{
+    int ij1 = 1, ij2 = ny - 2; /* 0-based jj=2..npjglo-1 */
+    if (ny <= 1) { ij1 = 0; ij2 = 0; }
+#pragma omp parallel
+    {
+        double *tmp = faithful ? (double *)malloc(sizeof(double) * (size_t)nbins * nx) : NULL;
+#pragma omp for schedule(runtime)
+        for (int j = ij1; j <= ij2; ++j) {
+            if (faithful) {
+                memset(tmp, 0, sizeof(double) * (size_t)nbins * nx);
+                for (int i = 1; i <= nx - 2; ++i) {
+                    size_t c = (size_t)j * nx + i;
+                    int ib = ibin[c] - 1;
+                    float p = zv[c] * zarea[c];
+                    tmp[(size_t)i * nbins + ib] = tmp[(size_t)i * nbins + ib] - (double)p;
+                }
+                for (int b = 0; b < nb; ++b)
+                    for (int bin = 0; bin < nbins; ++bin) {
+                        double acc = dmoc[((size_t)j * nbins + bin) * nb + b];
+                        for (int i = 1; i <= nx - 2; ++i)
+                            acc = acc + tmp[(size_t)i * nbins + bin] * (double)ibmask[((size_t)j * nx + i) * nb + b];
+                        dmoc[((size_t)j * nbins + bin) * nb + b] = acc;
+                    }
+            } else {
+                for (int i = 1; i <= nx - 2; ++i) {
+                    size_t c = (size_t)j * nx + i;
+                    int ib = ibin[c] - 1;
+                    float p = zv[c] * zarea[c];
+                    double t = 0.0 - (double)p;
+                    for (int b = 0; b < nb; ++b)
+                        dmoc[((size_t)j * nbins + ib) * nb + b] += t * (double)ibmask[c * nb + b];
+                }
+            }
+        }
+        free(tmp);
+    }
+}
+
+/* a11. bin cumsum -- src/cdfmocsig.f90:471-475 (1.e6 is REAL(4), exactly 10^6). */
+void oracle_mocsig_cumsum(int ny, int nb, int nbins, double *dmoc)
+{
+    for (int j = 0; j < ny; ++j)
+        for (int b = 0; b < nb; ++b) dmoc[((size_t)j * nbins + (nbins - 1)) * nb + b] /= 1.0e6;
+    for (int bin = nbins - 2; bin >= 0; --bin)
+        for (int j = 0; j < ny; ++j)
+            for (int b = 0; b < nb; ++b) {
+                size_t o = ((size_t)j * nbins + bin) * nb + b;
+                size_t o1 = ((size_t)j * nbins + bin + 1) * nb + b;
+                dmoc[o] = dmoc[o1] + dmoc[o] / 1.0e6;
+            }
+}
+
+/* Whole cdfmocsig record -- src/cdfmocsig.f90:366-475.
+ * zv,zt,zs: raw file values for levels 1..nz-1, (nz-1,ny,nx); e3v: UNmasked (nz,ny,nx) (or per record with -vvl).
+ * zveiv may be NULL.  ibin_out (optional, (nz-1,ny,nx) int32) receives the bin of every cell for bit-exact checks. */
+void oracle_cdfmocsig_record(int nx, int ny, int nz, int nb, int nbins, float sigmin, float sigstp, float pref, int eos,
+                             const float *e1v, const float *e3v, const int16_t *ibmask, float zspv, float zspt,
+                             float zsps, const float *zv_in, const float *zt_in, const float *zs_in,
+                             const float *zveiv_in, int faithful, double *dmoc, int32_t *ibin_out)
+{
+    size_t n = (size_t)nx * ny;
+    float *zv = malloc(4 * n), *zt = malloc(4 * n), *zs = malloc(4 * n), *zarea = malloc(4 * n);
+    int16_t *itmask = malloc(2 * n);
+    int32_t *ibin = malloc(4 * n);
+    double *dens = malloc(8 * n);
+    memset(dmoc, 0, sizeof(double) * (size_t)nb * nbins * ny);
+    for (int k = 0; k < nz - 1; ++k) {
+        memcpy(zv, zv_in + k * n, 4 * n);
+        memcpy(zt, zt_in + k * n, 4 * n);
+        memcpy(zs, zs_in + k * n, 4 * n);
+        oracle_mocsig_level_prep(nx, ny, zv, zt, zs, zveiv_in ? zveiv_in + k * n : NULL, e1v, e3v + k * n, zspv, zspt,
+                                 zsps, pref, eos, sigmin, sigstp, nbins, zarea, itmask, ibin, dens);
+        if (ibin_out) memcpy(ibin_out + k * n, ibin, 4 * n);
+        oracle_mocsig_level_accum(nx, ny, nb, nbins, zv, zarea, ibin, ibmask, faithful, dmoc);
+    }
+    oracle_mocsig_cumsum(ny, nb, nbins, dmoc);
+    free(zv); free(zt); free(zs); free(zarea); free(itmask); free(ibin); free(dens);
+}
+
+/* output conversion -- src/cdfmocsig.f90:478-483: out[b][bin][j] = REAL(dmoc(b,bin,j)); no inp0. */
+void oracle_cdfmocsig_output(int ny, int nb, int nbins, const double *dmoc, float *out)
+{
+    for (int b = 0; b < nb; ++b)
+        for (int bin = 0; bin < nbins; ++bin)
+            for (int j = 0; j < ny; ++j)
+                out[((size_t)b * nbins + bin) * ny + j] = (float)dmoc[((size_t)j * nbins + bin) * nb + b];
+}

@@ -1,0 +1,184 @@
+"""Independent NumPy restatement of the cdfmoc / cdfmocsig hot path (TEST INFRASTRUCTURE ONLY).
+
+Second, differently-structured restatement of the same reference loops as oracle/cdf_oracle.c.  It exists so
+that the C oracle is checked by something that shares no code with it: the polynomial EOS is evaluated here
+from the (i,j,k) coefficient table by a generic nested-Horner routine (the C file spells the expression out),
+and the zonal sums use sequential ``np.cumsum`` prefix sums.  The two must agree bit for bit
+(tests/test_oracle_cross.py).  Nothing in the product path imports this module.
+
+Array conventions: C-order ``[k][j][i]`` (== Fortran ``(i,j,k)``), masks ``[j][i][b]`` int16,
+``dmoc`` cdfmoc ``[k][j][b]`` float64, cdfmocsig ``[j][bin][b]`` float64.
+
+Reference lines: src/cdfmoc.f90:325-336,352-388,520-551,590-594; src/cdfmocsig.f90:265-304,374-475;
+src/eos.f90:207-279,408-466,661-684,842-882.
+"""
+from __future__ import annotations
+
+import re
+from pathlib import Path
+
+import numpy as np
+
+_HDR = Path(__file__).resolve().parent.parent / "include" / "cdf_eos_coeffs.h"
+
+
+def _load_coeffs():
+    txt = _HDR.read_text()
+    tabs = {}
+    for name in ("EOS80", "TEOS10"):
+        body = txt.split("CDF_%s_COEF[CDF_EOS_NCOEF] = {" % name)[1].split("};")[0]
+        d = {}
+        for m in re.finditer(r"([-+0-9.eE]+),\s*/\*\s*EOS(\d)(\d)(\d)\s*\*/", body):
+            d[(int(m.group(2)), int(m.group(3)), int(m.group(4)))] = float(m.group(1))
+        tabs[name] = d
+    r0 = [float(x) for x in txt.split("CDF_EOS_R0[6] = {")[1].split("}")[0].split(",")]
+    return tabs, r0
+
+
+_COEF, _R0 = _load_coeffs()
+_PARAMS = {"EOS80": (20.0, 1.0 / 40.0), "TEOS10": (32.0, 0.875 / 35.16504)}
+
+
+def _poly_k(E, k, t, s):
+    """One of dlr0..dlr3 (eos.f90:858-877) with the reference's association:
+    acc = E[0,J,k];  for j=J-1..0:  acc = (acc*t + Q_j) + E[0,j,k],  Q_j = (((E[I]*s+E[I-1])*s ...+E[1])*s."""
+    js = sorted({j for (i, j, kk) in E if kk == k})
+    J = js[-1]
+    acc = np.full_like(t, E[(0, J, k)])
+    for j in range(J - 1, -1, -1):
+        I = max(i for (i, jj, kk) in E if kk == k and jj == j)
+        q = np.full_like(s, E[(I, j, k)])
+        for i in range(I - 1, 0, -1):
+            q = q * s + E[(i, j, k)]
+        q = q * s
+        acc = (acc * t + q) + E[(0, j, k)]
+    return acc
+
+
+def eos_dlr(t32, s32, depth32, teos10=False):
+    E = _COEF["TEOS10" if teos10 else "EOS80"]
+    rdeltaS, r1_S0 = _PARAMS["TEOS10" if teos10 else "EOS80"]
+    t = np.asarray(t32, np.float32).astype(np.float64) * (1.0 / 40.0)
+    s = np.sqrt(np.abs(np.asarray(s32, np.float32).astype(np.float64) + rdeltaS) * r1_S0)
+    h = np.float64(np.float32(depth32)) * 1.0e-4
+    r3, r2, r1, r0 = (_poly_k(E, k, t, s) for k in (3, 2, 1, 0))
+    return ((r3 * h + r2) * h + r1) * h + r0
+
+
+def sigmai_dep(t32, s32, pref32, teos10=False):
+    """eos.f90:842-882."""
+    h = np.float64(np.float32(pref32)) * 1.0e-4
+    R = _R0
+    dlref = (((((R[5] * h + R[4]) * h + R[3]) * h + R[2]) * h + R[1]) * h + R[0]) * h
+    dlr = eos_dlr(t32, s32, pref32, teos10)
+    dltm = np.where(np.asarray(s32, np.float32) == np.float32(0), 0.0, 1.0)
+    return (dlr + dlref - 1000.0) * dltm
+
+
+def sigmantr(t32, s32):
+    """eos.f90:661-684."""
+    t = np.asarray(t32, np.float32).astype(np.float64)
+    s = np.asarray(s32, np.float32).astype(np.float64)
+    sr = np.sqrt(np.abs(s))
+    r1 = ((-4.3159255086706703e-4 * t + 8.1157118782170051e-2) * t + 2.2280832068441331e-1) * t + 1002.3063688892480
+    r2 = (-1.7052298331414675e-7 * s - 3.1710675488863952e-3 * t - 1.0304537539692924e-4) * s
+    r3 = (((-2.3850178558212048e-9 * t - 1.6212552470310961e-7) * t + 7.8717799560577725e-5) * t
+          + 4.3907692647825900e-5) * t + 1.0
+    r4 = ((-2.2744455733317707e-9 * t * t + 6.0399864718597388e-6) * t - 5.1268124398160734e-4) * s
+    r5 = (-1.3409379420216683e-9 * t * t - 3.6138532339703262e-5) * s * sr
+    return (r1 + r2) / (r3 + r4 + r5) - 1000.0
+
+
+def basin_masks(vmask1, atl=None, ind=None, pac=None, zero_edges=True):
+    """cdfmoc.f90:325-336.  Inputs REAL(4) (ny,nx); returns int16 (ny,nx,nb)."""
+    ny, nx = vmask1.shape
+    nb = 5 if atl is not None else 1
+    m = np.zeros((ny, nx, nb), np.int16)
+    m[:, :, 0] = np.trunc(vmask1).astype(np.int16)
+    if nb == 5:
+        m[:, :, 1] = np.trunc(atl).astype(np.int16)
+        m[:, :, 3] = np.trunc(ind).astype(np.int16)
+        m[:, :, 4] = np.trunc(pac).astype(np.int16)
+        ssum = (m[:, :, 4] + m[:, :, 3]).astype(np.int16)
+        m[:, :, 2] = np.where(ssum > 0, np.int16(1), ssum)
+    if zero_edges:
+        m[:, 0, 0] = 0
+        m[:, nx - 1, 0] = 0
+    return m
+
+
+def mask_e3v(e3v_file, vmask):
+    """cdfmoc.f90:590-594."""
+    return (e3v_file.astype(np.float32) * np.trunc(vmask).astype(np.int16).astype(np.float32)).astype(np.float32)
+
+
+def cdfmoc_record(e1v, e3m, ibmask, zv):
+    """cdfmoc.f90:352-388.  e1v (ny,nx) f32; e3m (nz,ny,nx) f32; ibmask (ny,nx,nb) i16; zv (nz-1,ny,nx) f32.
+    Returns dmoc (nz,ny,nb) f64 (scanned, Sv)."""
+    nz, ny, nx = e3m.shape
+    nb = ibmask.shape[2]
+    dmoc = np.zeros((nz, ny, nb), np.float64)
+    mf = ibmask.astype(np.float32)
+    for k in range(nz - 1):
+        a = (e1v * e3m[k]).astype(np.float32)
+        for b in range(nb):
+            t = ((a * mf[:, :, b]).astype(np.float32) * zv[k]).astype(np.float32)
+            # 0 - t0 - t1 - ... == -(t0 + t1 + ...) bit for bit (round-to-nearest is sign-symmetric)
+            dmoc[k, :, b] = -np.cumsum(t.astype(np.float64), axis=1)[:, -1]
+    dmoc = dmoc + 0.0  # normalise -0.0
+    for k in range(nz - 2, -1, -1):
+        dmoc[k] = dmoc[k + 1] + dmoc[k] / 1.0e6
+    return dmoc
+
+
+def cdfmoc_output(dmoc):
+    """cdfmoc.f90:520-551 -> (nvar, nz, ny) f32, inp0 last when nb==5."""
+    nz, ny, nb = dmoc.shape
+    outs = [dmoc[:, :, b].astype(np.float32) for b in range(nb)]
+    if nb >= 5:
+        outs.append((dmoc[:, :, 0] - dmoc[:, :, 1]).astype(np.float32))
+    return np.stack(outs)
+
+
+def sigma_axis(nbins, sigmin, sigstp):
+    """cdfmocsig.f90:302-304 in REAL(4)."""
+    n = np.arange(1, nbins + 1, dtype=np.float32)
+    return (np.float32(sigmin) + ((n - np.float32(0.5)) * np.float32(sigstp)).astype(np.float32)).astype(np.float32)
+
+
+def mocsig_bins(zt, zs, zsps, pref, eos, sigmin, sigstp, nbins):
+    """cdfmocsig.f90:393-403 on already-scrubbed zt, zs.  eos: 0 EOS80, 1 TEOS10, 2 neutral."""
+    itmask = np.where(zs == np.float32(zsps), 0, 1).astype(np.int16)
+    dens = sigmantr(zt, zs) if eos == 2 else sigmai_dep(zt, zs, pref, teos10=(eos == 1))
+    zttmp = (dens * itmask.astype(np.float64)).astype(np.float32)
+    q = ((zttmp - np.float32(sigmin)).astype(np.float32) / np.float32(sigstp)).astype(np.float32)
+    ib = np.trunc(q).astype(np.int64)
+    ib = np.minimum(np.maximum(ib, 1), nbins).astype(np.int32)
+    return ib, itmask, dens
+
+
+def cdfmocsig_record(e1v, e3v, ibmask, zv, zt, zs, spv, spt, sps, pref, eos, sigmin, sigstp, nbins, zveiv=None):
+    """cdfmocsig.f90:366-475.  Returns (dmoc (ny,nbins,nb) f64 scanned, ibin (nz-1,ny,nx) int32)."""
+    nzm1, ny, nx = zv.shape
+    nb = ibmask.shape[2]
+    H = np.zeros((ny, nbins, nb), np.float64)
+    bins = np.zeros((nzm1, ny, nx), np.int32)
+    j1, j2 = (1, ny - 2) if ny > 1 else (0, 0)
+    for k in range(nzm1):
+        v = np.where(zv[k] == np.float32(spv), np.float32(0), zv[k]).astype(np.float32)
+        if zveiv is not None:
+            v = (v + zveiv[k]).astype(np.float32)
+        t = np.where(zt[k] == np.float32(spt), np.float32(0), zt[k]).astype(np.float32)
+        s = np.where(zs[k] == np.float32(sps), np.float32(0), zs[k]).astype(np.float32)
+        area = (e1v * e3v[k]).astype(np.float32)
+        ib, _, _ = mocsig_bins(t, s, sps, pref, eos, sigmin, sigstp, nbins)
+        bins[k] = ib
+        p = (v * area).astype(np.float32)
+        contrib = 0.0 - p.astype(np.float64)
+        for j in range(j1, j2 + 1):
+            for i in range(1, nx - 1):  # sequential, i ascending: the order the reference sums in
+                H[j, ib[j, i] - 1, :] += contrib[j, i] * ibmask[j, i, :].astype(np.float64)
+    H[:, nbins - 1, :] = H[:, nbins - 1, :] / 1.0e6
+    for b in range(nbins - 2, -1, -1):
+        H[:, b, :] = H[:, b + 1, :] + H[:, b, :] / 1.0e6
+    return H, bins
