@@ -1,0 +1,66 @@
+"""Build recipe of libcdfgpu.so (the C-ABI CUDA library) -- sm_100a only, in-tree, no JIT cache.
+
+    python -m cdftools_b200.build            # builds cdftools_b200/libcdfgpu.so if sources are newer
+    python -m cdftools_b200.build --force
+
+nvcc cross-compiles without a GPU.  Flags that matter for parity:
+  -fmad=false            no implicit FMA contraction in device code (the reference's gfortran -O build on
+                         baseline x86-64 emits none; the sigma-bin assignment must be bit-exact)
+  -Xcompiler -ffp-contract=off   same for the host-side reference-profile polynomial
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+SO = PKG / "libcdfgpu.so"
+SOURCES = [CSRC / "api.cu"]
+DEPS = [CSRC / n for n in ("api.cu", "api_mocsig.inc", "common.cuh", "moc_kernel.cuh", "mocsig_kernel.cuh")] + [
+    PKG.parent / "include" / "cdfgpu.h", PKG.parent / "include" / "cdf_eos_coeffs.h"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-O2",
+    "-Xptxas", "-v",
+    "-shared", "-cudart", "static",
+]
+
+
+def nvcc_path() -> str:
+    for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and Path(c).exists():
+            return c
+    raise RuntimeError("nvcc not found: libcdfgpu.so cannot be built (there is no CPU fallback)")
+
+
+def needs_build() -> bool:
+    if not SO.exists():
+        return True
+    t = SO.stat().st_mtime
+    return any(d.stat().st_mtime > t for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return SO
+    cmd = [nvcc_path(), *NVCC_FLAGS, "-ccbin", "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++",
+           "-o", str(SO), *map(str, SOURCES)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log = r.stdout + r.stderr
+    (PKG / "build.log").write_text(" ".join(cmd) + "\n" + log)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + log[-4000:])
+    if verbose:
+        print(log)
+    return SO
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose=True)
+    print("built", p)

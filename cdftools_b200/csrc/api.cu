@@ -1,0 +1,414 @@
+// api.cu -- the C ABI of libcdfgpu.so (include/cdfgpu.h): context, record pipeline (pinned host buffer ->
+// side-stream H2D -> fused kernel -> D2H), and the setup-time preparation of the resident mesh/mask fields.
+// No CPU compute fallback exists anywhere in this file: every entry point needs a CUDA device.
+#include <stdlib.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "moc_kernel.cuh"
+#include "mocsig_kernel.cuh"
+
+namespace cdfgpu {
+
+char g_errbuf[512] = "";
+
+struct Ctx {
+    bool inited = false;
+    int device = 0;
+    int nslots = 3;
+    int sm_count = 0;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr, s_d2h = nullptr;
+    unsigned long long launches = 0;
+};
+static Ctx g;
+
+struct Workspace {  // scheduling counters of one stream-ordered sequence of launches
+    int *d_tickets = nullptr;  // [2]
+    int *d_col = nullptr;      // [ny]
+    int parity = 0;
+};
+
+struct Slot {
+    float *d_in[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // zv | zv,zt,zs,zveiv,e3v_vvl
+    double *d_out = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    bool used = false;
+    int jt = -1;
+};
+
+static int make_ws(Workspace &w, int ny)
+{
+    CDF_CUDA(cudaMalloc(&w.d_tickets, 2 * sizeof(int)));
+    CDF_CUDA(cudaMalloc(&w.d_col, (size_t)ny * sizeof(int)));
+    CDF_CUDA(cudaMemset(w.d_tickets, 0, 2 * sizeof(int)));
+    CDF_CUDA(cudaMemset(w.d_col, 0, (size_t)ny * sizeof(int)));
+    w.parity = 0;
+    return CDFGPU_OK;
+}
+static void free_ws(Workspace &w)
+{
+    cudaFree(w.d_tickets);
+    cudaFree(w.d_col);
+    w = Workspace();
+}
+static int make_slot_events(Slot &s)
+{
+    CDF_CUDA(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+    CDF_CUDA(cudaEventCreate(&s.ev_k0));
+    CDF_CUDA(cudaEventCreate(&s.ev_k1));
+    return CDFGPU_OK;
+}
+static void free_slot(Slot &s)
+{
+    for (auto &p : s.d_in) cudaFree(p);
+    cudaFree(s.d_out);
+    if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+    if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+    if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+    s = Slot();
+}
+
+// Packs (nb,nx,ny) INTEGER(2) masks into one byte per cell and builds the 4 pre-shifted word planes.
+// Returns false if some mask value is not 0/1 (then only the general path is valid).
+static bool pack_masks(int nx, int ny, int nb, const int16_t *ibmask, int pitchw, std::vector<uint32_t> &words)
+{
+    bool binary = true;
+    std::vector<uint8_t> bits((size_t)nx * ny);
+    for (size_t c = 0; c < (size_t)nx * ny; ++c) {
+        uint8_t v = 0;
+        for (int b = 0; b < nb; ++b) {
+            const int16_t m = ibmask[c * nb + b];
+            if (m != 0 && m != 1) binary = false;
+            if (m != 0) v |= (uint8_t)(1u << b);
+        }
+        bits[c] = v;
+    }
+    words.assign((size_t)4 * ny * pitchw, 0u);
+    for (int s = 0; s < 4; ++s)
+        for (int j = 0; j < ny; ++j) {
+            uint32_t *row = words.data() + ((size_t)s * ny + j) * pitchw;
+            const uint8_t *brow = bits.data() + (size_t)j * nx;
+            for (int w = 0; w < pitchw; ++w) {
+                uint32_t x = 0;
+                for (int c = 0; c < 4; ++c) {
+                    const long i = 4L * w - s + c;
+                    if (i >= 0 && i < nx) x |= (uint32_t)brow[i] << (8 * c);
+                }
+                row[w] = x;
+            }
+        }
+    return binary;
+}
+
+// =================================================================================================== cdfmoc
+struct MocPlan {
+    bool ready = false;
+    int nx = 0, ny = 0, nz = 0, nb = 0, pitchw = 0, general = 0, chunk = 1;
+    float *d_e1v = nullptr, *d_e3m = nullptr, *d_area = nullptr;
+    uint32_t *d_maskw = nullptr;
+    int16_t *d_ibmask = nullptr;
+    int *d_flag = nullptr;
+    Workspace ws_int, ws_ext;
+    Slot slots[CDFGPU_MAX_SLOTS];
+    int grid = 0;
+    size_t smem = 0;
+    size_t in_elems() const { return (size_t)(nz - 1) * ny * nx; }
+    size_t out_elems() const { return (size_t)nz * ny * nb; }
+};
+static MocPlan moc;
+
+template <int NB>
+static int moc_launch_t(const MocParams &p, cudaStream_t st)
+{
+    if (moc.grid == 0) {
+        int occ = 0;
+        CDF_CUDA(cudaFuncSetAttribute(moc_zonal_scan_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)moc.smem));
+        CDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, moc_zonal_scan_kernel<NB>, kMocThreads, moc.smem));
+        if (occ < 1) return set_error(CDFGPU_ERR_ARG, "cdfmoc: kernel does not fit (nz*nb too large for shared memory)");
+        moc.grid = occ * g.sm_count;
+    }
+    moc_zonal_scan_kernel<NB><<<moc.grid, kMocThreads, moc.smem, st>>>(p);
+    CDF_CUDA(cudaGetLastError());
+    ++g.launches;
+    return CDFGPU_OK;
+}
+
+static int moc_launch(const float *d_zv, double *d_out, Workspace &ws, cudaStream_t st)
+{
+    MocParams p;
+    p.zv = d_zv;
+    p.area = moc.d_area;
+    p.maskw = moc.d_maskw;
+    p.ibmask = moc.d_ibmask;
+    p.out = d_out;
+    p.tickets = ws.d_tickets;
+    p.col_done = ws.d_col;
+    p.nx = moc.nx; p.ny = moc.ny; p.nz = moc.nz; p.pitchw = moc.pitchw;
+    p.parity = ws.parity;
+    p.chunk = moc.chunk;
+    p.general = moc.general;
+    ws.parity ^= 1;
+    switch (moc.nb) {
+    case 1: return moc_launch_t<1>(p, st);
+    case 2: return moc_launch_t<2>(p, st);
+    case 3: return moc_launch_t<3>(p, st);
+    case 4: return moc_launch_t<4>(p, st);
+    case 5: return moc_launch_t<5>(p, st);
+    case 6: return moc_launch_t<6>(p, st);
+    case 7: return moc_launch_t<7>(p, st);
+    case 8: return moc_launch_t<8>(p, st);
+    }
+    return set_error(CDFGPU_ERR_ARG, "cdfmoc: nb must be 1..8");
+}
+
+static int moc_build_area()
+{
+    const size_t nxy = (size_t)moc.nx * moc.ny;
+    CDF_CUDA(cudaMemsetAsync(moc.d_flag, 0, sizeof(int), g.s_compute));
+    dim3 grid((unsigned)std::min<size_t>((nxy + 255) / 256, 4096), (unsigned)(moc.nz - 1));
+    moc_prep_area_kernel<<<grid, 256, 0, g.s_compute>>>(moc.d_e1v, moc.d_e3m, moc.d_area, nxy, moc.d_flag);
+    CDF_CUDA(cudaGetLastError());
+    ++g.launches;
+    int flag = 0;
+    CDF_CUDA(cudaMemcpyAsync(&flag, moc.d_flag, sizeof(int), cudaMemcpyDeviceToHost, g.s_compute));
+    CDF_CUDA(cudaStreamSynchronize(g.s_compute));
+    if (flag) moc.general = 1;
+    return CDFGPU_OK;
+}
+
+}  // namespace cdfgpu
+
+using namespace cdfgpu;
+
+#define REQUIRE_INIT()                                                                           \
+    if (!g.inited) return set_error(CDFGPU_ERR_STATE, "cdfgpu_init has not been called")
+#define REQUIRE(cond, code, msg)                                                                 \
+    if (!(cond)) return set_error(code, msg)
+
+extern "C" {
+
+int cdfgpu_abi_version(void) { return 1; }
+
+const char *cdfgpu_strerror(int code)
+{
+    switch (code) {
+    case CDFGPU_OK: return "ok";
+    case CDFGPU_ERR_CUDA: return "CUDA runtime error";
+    case CDFGPU_ERR_ARG: return "invalid argument";
+    case CDFGPU_ERR_STATE: return "call order violated";
+    case CDFGPU_ERR_NOMEM: return "out of device or pinned memory";
+    case CDFGPU_ERR_NODEVICE: return "no CUDA device available (libcdfgpu has no CPU fallback)";
+    }
+    return "unknown error";
+}
+const char *cdfgpu_last_error(void) { return g_errbuf; }
+
+int cdfgpu_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        set_error(CDFGPU_ERR_NODEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return -CDFGPU_ERR_NODEVICE;
+    }
+    return n;
+}
+
+int cdfgpu_init(int device, int nslots)
+{
+    if (g.inited) return CDFGPU_OK;
+    const int n = cdfgpu_device_count();
+    if (n <= 0) {
+        char why[256];
+        snprintf(why, sizeof(why), "%.200s", n < 0 ? g_errbuf : "device count is 0");
+        return set_error(CDFGPU_ERR_NODEVICE, "no CUDA device visible: %s", why);
+    }
+    if (device < 0) {
+        const char *e = getenv("CDFGPU_DEVICE");
+        device = e ? atoi(e) : 0;
+    }
+    REQUIRE(device < n, CDFGPU_ERR_ARG, "cdfgpu_init: device ordinal out of range");
+    if (nslots == 0) {
+        const char *e = getenv("CDFGPU_SLOTS");
+        nslots = e ? atoi(e) : 3;
+    }
+    REQUIRE(nslots >= 1 && nslots <= CDFGPU_MAX_SLOTS, CDFGPU_ERR_ARG, "cdfgpu_init: nslots must be 1..8");
+    CDF_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CDF_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return set_error(CDFGPU_ERR_NODEVICE, "libcdfgpu is built for sm_100a only; device is %s", prop.name);
+    g.device = device;
+    g.nslots = nslots;
+    g.sm_count = prop.multiProcessorCount;
+    CDF_CUDA(cudaStreamCreateWithFlags(&g.s_compute, cudaStreamNonBlocking));
+    CDF_CUDA(cudaStreamCreateWithFlags(&g.s_copy, cudaStreamNonBlocking));
+    CDF_CUDA(cudaStreamCreateWithFlags(&g.s_d2h, cudaStreamNonBlocking));
+    g.launches = 0;
+    g.inited = true;
+    return CDFGPU_OK;
+}
+
+int cdfgpu_synchronize(void)
+{
+    REQUIRE_INIT();
+    CDF_CUDA(cudaStreamSynchronize(g.s_copy));
+    CDF_CUDA(cudaStreamSynchronize(g.s_compute));
+    CDF_CUDA(cudaStreamSynchronize(g.s_d2h));
+    return CDFGPU_OK;
+}
+
+int cdfgpu_finalize(void)
+{
+    if (!g.inited) return CDFGPU_OK;
+    cdfgpu_synchronize();
+    cdfmoc_gpu_teardown();
+    cdfmocsig_gpu_teardown();
+    cudaStreamDestroy(g.s_compute);
+    cudaStreamDestroy(g.s_copy);
+    cudaStreamDestroy(g.s_d2h);
+    g = Ctx();
+    return CDFGPU_OK;
+}
+
+void *cdfgpu_pinned_alloc(size_t nbytes)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        set_error(CDFGPU_ERR_NOMEM, "cudaHostAlloc: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+int cdfgpu_pinned_free(void *p)
+{
+    if (p) CDF_CUDA(cudaFreeHost(p));
+    return CDFGPU_OK;
+}
+unsigned long long cdfgpu_launch_count(void) { return g.launches; }
+
+// --------------------------------------------------------------------------------------------------- cdfmoc
+int cdfmoc_gpu_teardown(void)
+{
+    if (!moc.ready && !moc.d_area) return CDFGPU_OK;
+    if (g.inited) cdfgpu_synchronize();
+    cudaFree(moc.d_e1v); cudaFree(moc.d_e3m); cudaFree(moc.d_area); cudaFree(moc.d_maskw);
+    cudaFree(moc.d_ibmask); cudaFree(moc.d_flag);
+    free_ws(moc.ws_int); free_ws(moc.ws_ext);
+    for (auto &s : moc.slots) free_slot(s);
+    moc = MocPlan();
+    return CDFGPU_OK;
+}
+
+int cdfmoc_gpu_setup(int nx, int ny, int nz, int nb, const float *e1v, const float *e3v, const int16_t *ibmask)
+{
+    REQUIRE_INIT();
+    REQUIRE(nx >= 1 && ny >= 1 && nz >= 2, CDFGPU_ERR_ARG, "cdfmoc_gpu_setup: need nx,ny >= 1 and nz >= 2");
+    REQUIRE(nb >= 1 && nb <= CDFGPU_MAX_BASINS, CDFGPU_ERR_ARG, "cdfmoc_gpu_setup: nb must be 1..8");
+    REQUIRE(e1v && e3v && ibmask, CDFGPU_ERR_ARG, "cdfmoc_gpu_setup: null pointer");
+    cdfmoc_gpu_teardown();
+    moc.nx = nx; moc.ny = ny; moc.nz = nz; moc.nb = nb;
+    moc.pitchw = (nx + 6) / 4 + 1;
+    // rows shorter than ~16 KB are handed out two levels at a time to halve the ticket traffic
+    moc.chunk = (nx < 4096) ? 2 : 1;
+    const size_t nxy = (size_t)nx * ny;
+    CDF_CUDA(cudaMalloc(&moc.d_e1v, nxy * sizeof(float)));
+    CDF_CUDA(cudaMalloc(&moc.d_e3m, nxy * (size_t)(nz - 1) * sizeof(float)));
+    CDF_CUDA(cudaMalloc(&moc.d_area, nxy * (size_t)(nz - 1) * sizeof(float) + 16));
+    CDF_CUDA(cudaMalloc(&moc.d_ibmask, nxy * nb * sizeof(int16_t)));
+    CDF_CUDA(cudaMalloc(&moc.d_maskw, (size_t)4 * ny * moc.pitchw * sizeof(uint32_t)));
+    CDF_CUDA(cudaMalloc(&moc.d_flag, sizeof(int)));
+    int rc;
+    if ((rc = make_ws(moc.ws_int, ny))) return rc;
+    if ((rc = make_ws(moc.ws_ext, ny))) return rc;
+    std::vector<uint32_t> words;
+    const bool binary = pack_masks(nx, ny, nb, ibmask, moc.pitchw, words);
+    moc.general = binary ? 0 : 1;
+    CDF_CUDA(cudaMemcpy(moc.d_maskw, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CDF_CUDA(cudaMemcpy(moc.d_ibmask, ibmask, nxy * nb * sizeof(int16_t), cudaMemcpyHostToDevice));
+    CDF_CUDA(cudaMemcpy(moc.d_e1v, e1v, nxy * sizeof(float), cudaMemcpyHostToDevice));
+    CDF_CUDA(cudaMemcpy(moc.d_e3m, e3v, nxy * (size_t)(nz - 1) * sizeof(float), cudaMemcpyHostToDevice));
+    if ((rc = moc_build_area())) return rc;
+    moc.smem = (size_t)(kMocThreads / 32) * (nz - 1) * nb * sizeof(double);
+    moc.grid = 0;
+    for (int s = 0; s < g.nslots; ++s) {
+        if ((rc = make_slot_events(moc.slots[s]))) return rc;
+        CDF_CUDA(cudaMalloc(&moc.slots[s].d_in[0], moc.in_elems() * sizeof(float) + 16));
+        CDF_CUDA(cudaMalloc(&moc.slots[s].d_out, moc.out_elems() * sizeof(double)));
+    }
+    moc.ready = true;
+    return CDFGPU_OK;
+}
+
+int cdfmoc_gpu_set_e3v(const float *e3v)
+{
+    REQUIRE_INIT();
+    REQUIRE(moc.ready, CDFGPU_ERR_STATE, "cdfmoc_gpu_set_e3v: cdfmoc_gpu_setup has not been called");
+    REQUIRE(e3v, CDFGPU_ERR_ARG, "cdfmoc_gpu_set_e3v: null pointer");
+    // the area field is read by every kernel in flight: drain first (rare path, once per record with -vvl)
+    CDF_CUDA(cudaStreamSynchronize(g.s_compute));
+    CDF_CUDA(cudaMemcpy(moc.d_e3m, e3v, (size_t)moc.nx * moc.ny * (moc.nz - 1) * sizeof(float), cudaMemcpyHostToDevice));
+    return moc_build_area();
+}
+
+int cdfmoc_gpu_submit(int slot, int jt, const float *zv)
+{
+    REQUIRE_INIT();
+    REQUIRE(moc.ready, CDFGPU_ERR_STATE, "cdfmoc_gpu_submit: cdfmoc_gpu_setup has not been called");
+    REQUIRE(slot >= 0 && slot < g.nslots, CDFGPU_ERR_ARG, "cdfmoc_gpu_submit: slot out of range");
+    REQUIRE(zv, CDFGPU_ERR_ARG, "cdfmoc_gpu_submit: null pointer");
+    Slot &s = moc.slots[slot];
+    if (s.used) CDF_CUDA(cudaStreamWaitEvent(g.s_copy, s.ev_k1, 0));  // previous kernel on this slot has read d_in
+    CDF_CUDA(cudaMemcpyAsync(s.d_in[0], zv, moc.in_elems() * sizeof(float), cudaMemcpyHostToDevice, g.s_copy));
+    CDF_CUDA(cudaEventRecord(s.ev_h2d, g.s_copy));
+    CDF_CUDA(cudaStreamWaitEvent(g.s_compute, s.ev_h2d, 0));
+    CDF_CUDA(cudaEventRecord(s.ev_k0, g.s_compute));
+    int rc = moc_launch(s.d_in[0], s.d_out, moc.ws_int, g.s_compute);
+    if (rc) return rc;
+    CDF_CUDA(cudaEventRecord(s.ev_k1, g.s_compute));
+    s.used = true;
+    s.jt = jt;
+    return CDFGPU_OK;
+}
+
+int cdfmoc_gpu_fetch(int slot, double *dmoc)
+{
+    REQUIRE_INIT();
+    REQUIRE(moc.ready, CDFGPU_ERR_STATE, "cdfmoc_gpu_fetch: cdfmoc_gpu_setup has not been called");
+    REQUIRE(slot >= 0 && slot < g.nslots, CDFGPU_ERR_ARG, "cdfmoc_gpu_fetch: slot out of range");
+    REQUIRE(dmoc, CDFGPU_ERR_ARG, "cdfmoc_gpu_fetch: null pointer");
+    Slot &s = moc.slots[slot];
+    REQUIRE(s.used, CDFGPU_ERR_STATE, "cdfmoc_gpu_fetch: nothing was submitted on this slot");
+    CDF_CUDA(cudaStreamWaitEvent(g.s_d2h, s.ev_k1, 0));
+    CDF_CUDA(cudaMemcpyAsync(dmoc, s.d_out, moc.out_elems() * sizeof(double), cudaMemcpyDeviceToHost, g.s_d2h));
+    CDF_CUDA(cudaStreamSynchronize(g.s_d2h));
+    return CDFGPU_OK;
+}
+
+int cdfmoc_gpu_compute_device(const float *d_zv, double *d_dmoc, void *stream)
+{
+    REQUIRE_INIT();
+    REQUIRE(moc.ready, CDFGPU_ERR_STATE, "cdfmoc_gpu_compute_device: cdfmoc_gpu_setup has not been called");
+    REQUIRE(d_zv && d_dmoc, CDFGPU_ERR_ARG, "cdfmoc_gpu_compute_device: null pointer");
+    if (stream == nullptr) return moc_launch(d_zv, d_dmoc, moc.ws_int, g.s_compute);
+    return moc_launch(d_zv, d_dmoc, moc.ws_ext, (cudaStream_t)stream);
+}
+
+int cdfmoc_gpu_kernel_ms(int slot, float *ms)
+{
+    REQUIRE_INIT();
+    REQUIRE(moc.ready && slot >= 0 && slot < g.nslots && ms, CDFGPU_ERR_ARG, "cdfmoc_gpu_kernel_ms: bad argument");
+    Slot &s = moc.slots[slot];
+    REQUIRE(s.used, CDFGPU_ERR_STATE, "cdfmoc_gpu_kernel_ms: nothing was submitted on this slot");
+    CDF_CUDA(cudaEventSynchronize(s.ev_k1));
+    CDF_CUDA(cudaEventElapsedTime(ms, s.ev_k0, s.ev_k1));
+    return CDFGPU_OK;
+}
+
+}  // extern "C"
+
+#include "api_mocsig.inc"

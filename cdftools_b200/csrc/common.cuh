@@ -1,0 +1,62 @@
+// common.cuh -- shared helpers of libcdfgpu (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/cdfgpu.h"
+
+namespace cdfgpu {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---- error plumbing -------------------------------------------------------------------------------------------
+extern char g_errbuf[512];
+inline int set_error(int code, const char *fmt, const char *a = "", const char *b = "")
+{
+    snprintf(g_errbuf, sizeof(g_errbuf), fmt, a, b);
+    return code;
+}
+#define CDF_CUDA(call)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t e__ = (call);                                                                            \
+        if (e__ != cudaSuccess) {                                                                            \
+            snprintf(cdfgpu::g_errbuf, sizeof(cdfgpu::g_errbuf), "%s failed: %s (%s:%d)", #call,             \
+                     cudaGetErrorString(e__), __FILE__, __LINE__);                                           \
+            return (e__ == cudaErrorMemoryAllocation) ? CDFGPU_ERR_NOMEM                                     \
+                   : (e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver) ? CDFGPU_ERR_NODEVICE  \
+                                                                                      : CDFGPU_ERR_CUDA;     \
+        }                                                                                                    \
+    } while (0)
+
+// ---- device helpers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// L2 policy for data that is read exactly once (the record and the resident area field): evict first, so the
+// small mask planes that every level re-reads stay in L2.
+__device__ __forceinline__ uint64_t make_evict_first_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// streaming 16-byte load: read-only path, no L1 allocation, L2 evict-first
+__device__ __forceinline__ float4 ld_stream_f4(const float4 *p, uint64_t pol)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+}  // namespace cdfgpu

@@ -1,0 +1,205 @@
+// moc_kernel.cuh -- K1: depth-space MOC.  Replaces the loop nest src/cdfmoc.f90:352-388.
+//
+//   T(b,j,k) = sum_i -dble( fl32( fl32( fl32(e1v*e3m) * real(ibmask(b)) ) * zv ) )       (cdfmoc.f90:373-374)
+//   psi(b,j,nz) = 0 ; psi(b,j,k) = psi(b,j,k+1) + T(b,j,k)/1.d6 , k = nz-1..1            (cdfmoc.f90:385)
+//
+// Design (HBM-bound streaming reduction, 8 algorithmic bytes per level-cell):
+//   * `area` = fl32(e1v*e3m) is precomputed once at setup and stays resident; the five basin masks are packed
+//     into one byte per (j,i) (bit b = basin b) and kept L2-resident, so a record costs 4 B (V) + 4 B (area).
+//   * One warp owns one (j,k) row at a time; rows are handed out dynamically (j-major, atomic ticket, prefetched
+//     one row ahead) to a persistent grid sized to the SM count.  Loads are 16-byte streaming loads on the
+//     FLAT array (rows of the ORCA grids are only 8-byte aligned, so vectors may straddle row ends): the mask
+//     byte-planes are stored in 4 pre-shifted copies whose out-of-row bytes are zero, which both aligns the
+//     mask words with the float4 lanes and masks off the neighbours' cells for free.
+//   * Per cell: one FMUL (fl32 product, exactly the reference's chain when the mask is 0/1), one F2F to fp64,
+//     and one predicated DADD per basin.  fp64 lane partials -> warp shuffle tree.
+//   * Exactness guard: the fast path equals the reference chain whenever masks are in {0,1} and the products are
+//     finite.  A NaN/Inf anywhere in the row is detected for free (fma(p,0,flag)) and the warp then redoes the
+//     row with the literal multiply chain (row_sums_general), which is also the path for non-binary masks.
+//   * The raw sums go to the output slab; the warp that completes the last level of a column j performs the
+//     bottom-up recurrence in the reference's sequential order (lanes = basins) -- no second kernel.
+#pragma once
+#include "common.cuh"
+
+namespace cdfgpu {
+
+struct MocParams {
+    const float *__restrict__ zv;       // (nz-1, ny, nx) one time record, levels 1..nz-1
+    const float *__restrict__ area;     // (nz-1, ny, nx) fl32(e1v*e3m)
+    const uint32_t *__restrict__ maskw; // [4][ny][pitchw] packed basin bits, copy s shifted by s cells
+    const int16_t *__restrict__ ibmask; // (ny, nx, nb) for the general path
+    double *__restrict__ out;           // (nz, ny, nb)
+    int *tickets;                       // [2] row tickets (ping-pong between launches)
+    int *col_done;                      // [ny] rows finished per column j (self-resetting)
+    int nx, ny, nz, pitchw;
+    int parity;                         // launch parity selecting tickets[parity]
+    int chunk;                          // consecutive levels of one column handed out per ticket
+    int general;                        // 1: masks are not 0/1 (or area not finite) -> literal chain everywhere
+};
+
+constexpr int kMocThreads = 256;
+constexpr int kMocUnroll = 4;
+
+template <int NB>
+__device__ __forceinline__ void moc_cell(float a, float v, uint32_t mbits, double (&acc)[NB], float &badf)
+{
+    const float p = __fmul_rn(a, v);
+    badf = __fmaf_rn(p, 0.0f, badf);  // NaN iff p is NaN/Inf, else unchanged
+    const double dp = (double)p;
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+        if (mbits & (1u << b)) acc[b] -= dp;
+}
+
+// Fast path: exact for 0/1 masks and finite products.  Returns lane partial sums.
+template <int NB>
+__device__ __forceinline__ void row_sums_fast(const MocParams &p, int j, int k, int lane, uint64_t pol,
+                                              double (&acc)[NB], float &badf)
+{
+    const size_t e0 = ((size_t)k * p.ny + j) * (size_t)p.nx;
+    const int s = (int)(e0 & 3);
+    const size_t a0 = e0 - s;
+    const int nvec = (s + p.nx + 3) >> 2;
+    const float4 *__restrict__ v4 = reinterpret_cast<const float4 *>(p.zv + a0);
+    const float4 *__restrict__ a4 = reinterpret_cast<const float4 *>(p.area + a0);
+    const uint32_t *__restrict__ mw = p.maskw + ((size_t)s * p.ny + j) * p.pitchw;
+
+    for (int v0 = lane; v0 < nvec; v0 += kWarp * kMocUnroll) {
+        float4 vv[kMocUnroll], aa[kMocUnroll];
+        uint32_t mm[kMocUnroll];
+#pragma unroll
+        for (int u = 0; u < kMocUnroll; ++u) {
+            const int vi = v0 + u * kWarp;
+            if (vi < nvec) {
+                vv[u] = ld_stream_f4(v4 + vi, pol);
+                aa[u] = ld_stream_f4(a4 + vi, pol);
+                mm[u] = __ldg(mw + vi);
+            } else {
+                vv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                aa[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                mm[u] = 0u;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kMocUnroll; ++u) {
+            moc_cell<NB>(aa[u].x, vv[u].x, mm[u], acc, badf);
+            moc_cell<NB>(aa[u].y, vv[u].y, mm[u] >> 8, acc, badf);
+            moc_cell<NB>(aa[u].z, vv[u].z, mm[u] >> 16, acc, badf);
+            moc_cell<NB>(aa[u].w, vv[u].w, mm[u] >> 24, acc, badf);
+        }
+    }
+}
+
+// General path: the literal chain of cdfmoc.f90:373-374 with INTEGER(2) mask values (any value, NaN/Inf safe).
+// Handles the whole row (sums, warp reduction, store of the raw sums) so that the fast path keeps its
+// accumulators in registers.
+template <int NB>
+__device__ __noinline__ void row_general_store(const MocParams &p, int j, int k, int lane)
+{
+    const size_t e0 = ((size_t)k * p.ny + j) * (size_t)p.nx;
+    double acc[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) acc[b] = 0.0;
+    for (int i = lane; i < p.nx; i += kWarp) {
+        const float a = p.area[e0 + i];
+        const float v = p.zv[e0 + i];
+        const int16_t *m = p.ibmask + ((size_t)j * p.nx + i) * NB;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const float t = __fmul_rn(__fmul_rn(a, (float)m[b]), v);
+            acc[b] -= (double)t;
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const double t = warp_sum(acc[b]);
+        if (lane == b) p.out[((size_t)k * p.ny + j) * NB + b] = t;
+    }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(kMocThreads, 3) moc_zonal_scan_kernel(const MocParams p)
+{
+    extern __shared__ double s_scan[];  // [warps][(nz-1)*NB]
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const int nzm1 = p.nz - 1;
+    const uint64_t pol = make_evict_first_policy();
+    const int chunks_per_col = (nzm1 + p.chunk - 1) / p.chunk;
+    const int nunits = p.ny * chunks_per_col;
+    int *ticket = p.tickets + p.parity;
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.tickets[p.parity ^ 1] = 0;  // re-arm the next launch's counter
+
+    int u = 0;
+    if (lane == 0) u = atomicAdd(ticket, 1);
+    u = __shfl_sync(kFull, u, 0);
+    while (u < nunits) {
+        int unext = 0;
+        if (lane == 0) unext = atomicAdd(ticket, 1);  // prefetch the next ticket; latency hidden by the row below
+        const int j = u / chunks_per_col;
+        const int k0 = (u - j * chunks_per_col) * p.chunk;
+        const int k1 = min(k0 + p.chunk, nzm1);
+        for (int k = k0; k < k1; ++k) {
+            double acc[NB];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) acc[b] = 0.0;
+            bool bad = p.general != 0;
+            if (!bad) {
+                float badf = 0.0f;
+                row_sums_fast<NB>(p, j, k, lane, pol, acc, badf);
+                bad = __any_sync(kFull, badf != badf);
+            }
+            if (bad) {
+                row_general_store<NB>(p, j, k, lane);
+            } else {
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const double t = warp_sum(acc[b]);
+                    if (lane == b) p.out[((size_t)k * p.ny + j) * NB + b] = t;
+                }
+            }
+        }
+        // publish the rows, then count them; the warp that completes column j integrates it vertically
+        __syncwarp();
+        int done = 0;
+        if (lane == 0) {
+            __threadfence();
+            done = atomicAdd(p.col_done + j, k1 - k0) + (k1 - k0);
+        }
+        done = __shfl_sync(kFull, done, 0);
+        if (done == nzm1) {
+            __threadfence();
+            double *sc = s_scan + (size_t)warp * nzm1 * NB;
+            for (int t = lane; t < nzm1 * NB; t += kWarp) {
+                const int k = t / NB, b = t - k * NB;
+                sc[t] = __ldcg(p.out + ((size_t)k * p.ny + j) * NB + b) / 1.0e6;  // dmoc(:,jj,jk)/1.d6
+            }
+            __syncwarp();
+            if (lane < NB) {
+                double psi = 0.0;
+                p.out[((size_t)nzm1 * p.ny + j) * NB + lane] = 0.0;  // dmoc(:,:,npk) stays 0
+                for (int k = nzm1 - 1; k >= 0; --k) {
+                    psi = psi + sc[k * NB + lane];  // dmoc(:,jj,jk+1) + dmoc(:,jj,jk)/1.d6
+                    p.out[((size_t)k * p.ny + j) * NB + lane] = psi;
+                }
+            }
+            if (lane == 0) p.col_done[j] = 0;  // self-reset for the next launch
+            __syncwarp();
+        }
+        u = __shfl_sync(kFull, unext, 0);
+    }
+}
+
+// setup kernel: area = fl32(e1v * e3m) for levels 0..nz-2; flags non-finite products.
+__global__ void moc_prep_area_kernel(const float *__restrict__ e1v, const float *__restrict__ e3m,
+                                     float *__restrict__ area, size_t nxy, int *nonfinite)
+{
+    const size_t k = blockIdx.y;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < nxy; c += (size_t)gridDim.x * blockDim.x) {
+        const float a = __fmul_rn(e1v[c], e3m[k * nxy + c]);
+        area[k * nxy + c] = a;
+        if (!isfinite(a)) atomicOr(nonfinite, 1);
+    }
+}
+
+}  // namespace cdfgpu

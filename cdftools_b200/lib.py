@@ -1,0 +1,227 @@
+"""ctypes binding of libcdfgpu.so -- every call goes through the C ABI declared in include/cdfgpu.h.
+
+This is the Python twin of the Fortran ISO_C_BINDING module (cdftools_b200/fortran/cdfgpu_mod.f90): same entry
+points, same argument meaning.  There is no CPU implementation behind it: if the shared library is missing or no
+CUDA device is usable, the calls raise CdfGpuError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+SO_PATH = PKG / "libcdfgpu.so"
+
+EOS80, TEOS10, NEUTRAL = 0, 1, 2
+
+# name -> (restype, argtypes): the complete export list of include/cdfgpu.h (tests check both directions)
+_f32p, _f64p, _i16p, _i32p = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int16), C.POINTER(C.c_int32)
+SIGNATURES = {
+    "cdfgpu_init": (C.c_int, [C.c_int, C.c_int]),
+    "cdfgpu_finalize": (C.c_int, []),
+    "cdfgpu_synchronize": (C.c_int, []),
+    "cdfgpu_strerror": (C.c_char_p, [C.c_int]),
+    "cdfgpu_last_error": (C.c_char_p, []),
+    "cdfgpu_device_count": (C.c_int, []),
+    "cdfgpu_abi_version": (C.c_int, []),
+    "cdfgpu_pinned_alloc": (C.c_void_p, [C.c_size_t]),
+    "cdfgpu_pinned_free": (C.c_int, [C.c_void_p]),
+    "cdfgpu_launch_count": (C.c_ulonglong, []),
+    "cdfmoc_gpu_setup": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cdfmoc_gpu_set_e3v": (C.c_int, [C.c_void_p]),
+    "cdfmoc_gpu_submit": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
+    "cdfmoc_gpu_fetch": (C.c_int, [C.c_int, C.c_void_p]),
+    "cdfmoc_gpu_compute_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cdfmoc_gpu_kernel_ms": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
+    "cdfmoc_gpu_teardown": (C.c_int, []),
+    "cdfmocsig_gpu_setup": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                      C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                      C.c_int, C.c_int]),
+    "cdfmocsig_gpu_submit": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cdfmocsig_gpu_fetch": (C.c_int, [C.c_int, C.c_void_p]),
+    "cdfmocsig_gpu_compute_device": (C.c_int, [C.c_void_p] * 7),
+    "cdfmocsig_gpu_bins_device": (C.c_int, [C.c_void_p] * 4),
+    "cdfmocsig_gpu_kernel_ms": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
+    "cdfmocsig_gpu_teardown": (C.c_int, []),
+}
+
+
+class CdfGpuError(RuntimeError):
+    def __init__(self, code: int, where: str, text: str):
+        super().__init__(f"{where}: error {code}: {text}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """dlopen libcdfgpu.so and declare all prototypes.  Fails loudly if the library has not been built."""
+    global _lib
+    if _lib is None:
+        if not SO_PATH.exists():
+            raise CdfGpuError(-1, "load", f"{SO_PATH} is missing -- build it with `python -m cdftools_b200.build` "
+                                          "(there is no CPU fallback)")
+        lib = C.CDLL(str(SO_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def _chk(rc: int, where: str):
+    if rc != 0:
+        lib = load()
+        raise CdfGpuError(rc, where, (lib.cdfgpu_last_error() or b"").decode() or lib.cdfgpu_strerror(rc).decode())
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous ([k][j][i] == Fortran (i,j,k))"
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):  # torch tensor (host pinned or device)
+        assert a.is_contiguous()
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+def stream_handle(stream) -> int:
+    """cudaStream_t for the C ABI from a torch stream.  torch's default stream is handle 0, which the ABI reserves
+    for "the library's own compute stream"; map it to cudaStreamLegacy (0x1)."""
+    if stream is None:
+        return 0
+    h = int(stream.cuda_stream) if hasattr(stream, "cuda_stream") else int(stream)
+    return h if h != 0 else 1
+
+
+# ---- lifecycle -----------------------------------------------------------------------------------------------
+def init(device: int = -1, nslots: int = 0):
+    _chk(load().cdfgpu_init(device, nslots), "cdfgpu_init")
+
+
+def finalize():
+    if _lib is not None:
+        _chk(_lib.cdfgpu_finalize(), "cdfgpu_finalize")
+
+
+def synchronize():
+    _chk(load().cdfgpu_synchronize(), "cdfgpu_synchronize")
+
+
+def device_count() -> int:
+    return int(load().cdfgpu_device_count())
+
+
+def launch_count() -> int:
+    return int(load().cdfgpu_launch_count())
+
+
+class PinnedArray:
+    """A numpy view over a page-locked buffer from cdfgpu_pinned_alloc (what NF90_GET_VAR would fill)."""
+
+    def __init__(self, shape, dtype=np.float32):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.addr = load().cdfgpu_pinned_alloc(self.nbytes)
+        if not self.addr:
+            raise CdfGpuError(4, "cdfgpu_pinned_alloc", load().cdfgpu_last_error().decode())
+        buf = (C.c_char * self.nbytes).from_address(self.addr)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self.addr:
+            self.array = None
+            load().cdfgpu_pinned_free(self.addr)
+            self.addr = None
+
+
+# ---- cdfmoc ----------------------------------------------------------------------------------------------------
+def cdfmoc_setup(e1v, e3v_masked, ibmask):
+    """e1v (ny,nx) f32; e3v_masked (nz,ny,nx) f32 already * vmask (cdfmoc.f90:590-594); ibmask (ny,nx,nb) int16."""
+    nz, ny, nx = e3v_masked.shape
+    nb = ibmask.shape[2]
+    assert e1v.shape == (ny, nx) and ibmask.shape[:2] == (ny, nx)
+    assert e1v.dtype == np.float32 and e3v_masked.dtype == np.float32 and ibmask.dtype == np.int16
+    _chk(load().cdfmoc_gpu_setup(nx, ny, nz, nb, _ptr(e1v), _ptr(e3v_masked), _ptr(ibmask)), "cdfmoc_gpu_setup")
+    return (nz, ny, nb)
+
+
+def cdfmoc_set_e3v(e3v_masked):
+    _chk(load().cdfmoc_gpu_set_e3v(_ptr(e3v_masked)), "cdfmoc_gpu_set_e3v")
+
+
+def cdfmoc_submit(slot: int, jt: int, zv):
+    _chk(load().cdfmoc_gpu_submit(slot, jt, _ptr(zv)), "cdfmoc_gpu_submit")
+
+
+def cdfmoc_fetch(slot: int, out):
+    _chk(load().cdfmoc_gpu_fetch(slot, _ptr(out)), "cdfmoc_gpu_fetch")
+    return out
+
+
+def cdfmoc_compute_device(d_zv, d_dmoc, stream=None):
+    _chk(load().cdfmoc_gpu_compute_device(_ptr(d_zv), _ptr(d_dmoc), C.c_void_p(stream_handle(stream))),
+         "cdfmoc_gpu_compute_device")
+
+
+def cdfmoc_kernel_ms(slot: int) -> float:
+    ms = C.c_float()
+    _chk(load().cdfmoc_gpu_kernel_ms(slot, C.byref(ms)), "cdfmoc_gpu_kernel_ms")
+    return ms.value
+
+
+def cdfmoc_teardown():
+    _chk(load().cdfmoc_gpu_teardown(), "cdfmoc_gpu_teardown")
+
+
+# ---- cdfmocsig -------------------------------------------------------------------------------------------------
+def cdfmocsig_setup(e1v, e3v, ibmask, nz, nbins, sigmin, sigstp, pref, eos, spv=0.0, spt=0.0, sps=0.0,
+                    j_first_global=0, ny_global=None):
+    """e3v (>=nz-1,ny,nx) f32 UNmasked, or None with -vvl (then every submit brings e3v)."""
+    ny, nx = e1v.shape
+    nb = ibmask.shape[2]
+    assert e1v.dtype == np.float32 and ibmask.dtype == np.int16 and ibmask.shape[:2] == (ny, nx)
+    if e3v is not None:
+        assert e3v.dtype == np.float32 and e3v.shape[0] >= nz - 1 and e3v.shape[1:] == (ny, nx)
+    _chk(load().cdfmocsig_gpu_setup(nx, ny, nz, nb, int(nbins), float(sigmin), float(sigstp), float(pref), int(eos),
+                                    _ptr(e1v), _ptr(e3v), _ptr(ibmask), float(spv), float(spt), float(sps),
+                                    int(j_first_global), int(ny if ny_global is None else ny_global)),
+         "cdfmocsig_gpu_setup")
+    return (ny, int(nbins), nb)
+
+
+def cdfmocsig_submit(slot, jt, zv, zt, zs, zveiv=None, e3v_vvl=None):
+    _chk(load().cdfmocsig_gpu_submit(slot, jt, _ptr(zv), _ptr(zt), _ptr(zs), _ptr(zveiv), _ptr(e3v_vvl)),
+         "cdfmocsig_gpu_submit")
+
+
+def cdfmocsig_fetch(slot, out):
+    _chk(load().cdfmocsig_gpu_fetch(slot, _ptr(out)), "cdfmocsig_gpu_fetch")
+    return out
+
+
+def cdfmocsig_compute_device(d_zv, d_zt, d_zs, d_dmoc, d_zveiv=None, d_e3v_vvl=None, stream=None):
+    _chk(load().cdfmocsig_gpu_compute_device(_ptr(d_zv), _ptr(d_zt), _ptr(d_zs), _ptr(d_zveiv), _ptr(d_e3v_vvl),
+                                             _ptr(d_dmoc), C.c_void_p(stream_handle(stream))),
+         "cdfmocsig_gpu_compute_device")
+
+
+def cdfmocsig_bins_device(d_zt, d_zs, d_ibin, stream=None):
+    _chk(load().cdfmocsig_gpu_bins_device(_ptr(d_zt), _ptr(d_zs), _ptr(d_ibin), C.c_void_p(stream_handle(stream))),
+         "cdfmocsig_gpu_bins_device")
+
+
+def cdfmocsig_kernel_ms(slot: int) -> float:
+    ms = C.c_float()
+    _chk(load().cdfmocsig_gpu_kernel_ms(slot, C.byref(ms)), "cdfmocsig_gpu_kernel_ms")
+    return ms.value
+
+
+def cdfmocsig_teardown():
+    _chk(load().cdfmocsig_gpu_teardown(), "cdfmocsig_gpu_teardown")

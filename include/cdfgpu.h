@@ -1,0 +1,118 @@
+/*
+ * cdfgpu.h -- C ABI of libcdfgpu.so: the B200 (sm_100a) implementation of the CDFTOOLS meridional-overturning
+ * hot path (cdfmoc zonal transport integral + vertical scan; cdfmocsig fused EOS + density-class scatter-add).
+ *
+ * The reference (meom-group/CDFTOOLS) is Fortran 90 with no FFI: each tool is a monolithic PROGRAM.  This ABI is
+ * cut exactly around the two loop nests that are the hot path, so that a thin ISO_C_BINDING layer
+ * (cdftools_b200/fortran/cdfgpu_mod.f90) can replace them in place:
+ *
+ *     src/cdfmoc.f90:352-388      -> cdfmoc_gpu_submit / cdfmoc_gpu_fetch
+ *     src/cdfmocsig.f90:366-475   -> cdfmocsig_gpu_submit / cdfmocsig_gpu_fetch
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  Every entry point returns 0 (CDFGPU_OK) or a CDFGPU_ERR_* code;
+ *     cdfgpu_last_error() holds the text.  The Fortran host does `IF (ierr /= 0) STOP 97`.
+ *   - Arrays are passed in the reference's own memory order (Fortran column-major == C [k][j][i]):
+ *       e1v(nx,ny) REAL(4), e3v(nx,ny,nz) REAL(4), ibmask(nb,nx,ny) INTEGER(2) basin fastest,
+ *       zv/zt/zs(nx,ny,nz-1) REAL(4) (levels 1..nz-1 of one time record; level nz is never read,
+ *       src/cdfmoc.f90:355), dmoc(nb,ny,nz) REAL(8) (cdfmoc.f90:287), dmoc(nb,nbins,ny) REAL(8) (cdfmocsig.f90:313).
+ *   - The caller owns all host memory.  setup copies mesh/mask fields to the device (resident until teardown).
+ *     A buffer given to *_submit must stay untouched until the matching *_fetch returns.  Host buffers from
+ *     cdfgpu_pinned_alloc() make the H2D copy asynchronous (side stream, overlaps the previous record's kernel);
+ *     pageable memory works but the copy is then staged by the driver.
+ *   - One process drives one GPU (cdfgpu_init(device)).  Multi-GPU runs are one process per GPU; records
+ *     (time sharding) or latitude bands (band sharding: pass the band's rows, see j_first_global) are
+ *     distributed by the host layer and the per-rank slabs gathered there (NCCL) -- no data-path collective.
+ *   - Not re-entrant: call from one host thread (the reference's call sites are single-threaded).
+ *   - There is NO CPU fallback: without a usable CUDA device every call fails with CDFGPU_ERR_NODEVICE.
+ */
+#ifndef CDFGPU_H
+#define CDFGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDFGPU_OK 0
+#define CDFGPU_ERR_CUDA 1     /* a CUDA runtime call failed; see cdfgpu_last_error() */
+#define CDFGPU_ERR_ARG 2      /* invalid argument */
+#define CDFGPU_ERR_STATE 3    /* call order violated (no init / no setup / slot never submitted) */
+#define CDFGPU_ERR_NOMEM 4    /* device or pinned allocation failed */
+#define CDFGPU_ERR_NODEVICE 5 /* no CUDA device / driver */
+
+#define CDFGPU_EOS_EOS80 0   /* polynomial EOS-80  (eos_init default,  src/eos.f90:408-466) */
+#define CDFGPU_EOS_TEOS10 1  /* polynomial TEOS-10 (-teos10,           src/eos.f90:221-279) */
+#define CDFGPU_EOS_NEUTRAL 2 /* neutral density    (-ntr, sigmantr,    src/eos.f90:661-684) */
+
+#define CDFGPU_MAX_SLOTS 8
+#define CDFGPU_MAX_BASINS 8
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------- */
+/* Select the CUDA device (device < 0: $CDFGPU_DEVICE, else 0), create the compute and copy streams.
+ * nslots (1..CDFGPU_MAX_SLOTS, 0 = default 3) is the depth of the record pipeline. */
+int cdfgpu_init(int device, int nslots);
+int cdfgpu_finalize(void);
+int cdfgpu_synchronize(void);
+const char *cdfgpu_strerror(int code);
+const char *cdfgpu_last_error(void);
+int cdfgpu_device_count(void); /* >= 0, or -CDFGPU_ERR_* */
+int cdfgpu_abi_version(void);
+/* Page-locked host buffers for NF90_GET_VAR to fill (Fortran: c_f_pointer onto the returned address). */
+void *cdfgpu_pinned_alloc(size_t nbytes);
+int cdfgpu_pinned_free(void *p);
+/* Number of kernels this library has launched since cdfgpu_init (bench.py's gpu_launches). */
+unsigned long long cdfgpu_launch_count(void);
+
+/* ---- cdfmoc: depth-space MOC ------------------------------------------------------------------------------
+ * setup   replaces the one-time part of src/cdfmoc.f90:306,325-336,343-348:
+ *           e1v     (nx,ny)      cdfmoc.f90:306
+ *           e3v     (nx,ny,nz)   ALREADY multiplied by vmask(k) as get_e3v does (cdfmoc.f90:590-594)
+ *           ibmask  (nb,nx,ny)   assembled as cdfmoc.f90:325-336 (global i=1,nx already zeroed)
+ * set_e3v replaces the per-record reload under -vvl (cdfmoc.f90:339-348).
+ * submit  enqueues record jt: H2D of zv on the copy stream, then the fused zonal-integral + scan kernel.
+ * fetch   blocks until the slot's record is done and writes dmoc(nb,ny,nz) in Sv, already integrated from the
+ *         bottom (cdfmoc.f90:382-388); dmoc(:,:,nz) = 0.
+ * compute_device: same kernel on a record that is already in device memory (d_zv, d_dmoc device pointers,
+ *         `stream` a cudaStream_t or NULL for the library's compute stream); asynchronous. */
+int cdfmoc_gpu_setup(int nx, int ny, int nz, int nb, const float *e1v, const float *e3v, const int16_t *ibmask);
+int cdfmoc_gpu_set_e3v(const float *e3v);
+int cdfmoc_gpu_submit(int slot, int jt, const float *zv);
+int cdfmoc_gpu_fetch(int slot, double *dmoc);
+int cdfmoc_gpu_compute_device(const float *d_zv, double *d_dmoc, void *stream);
+int cdfmoc_gpu_kernel_ms(int slot, float *ms); /* device time of the slot's last kernel, CUDA events */
+int cdfmoc_gpu_teardown(void);
+
+/* ---- cdfmocsig: density-space MOC -------------------------------------------------------------------------
+ * setup   replaces src/cdfmocsig.f90:325,347-359 and fixes the binning (cdfmocsig.f90:265-304):
+ *           e3v (nx,ny,nz) is the UNmasked e3v of mesh_zgr (cdfmocsig.f90:388; pass e31d(k) planes for -full),
+ *           or NULL when every submit brings its own (-vvl).
+ *           zspv/zspt/zsps: missing values of V, T, S (getspval, cdfmocsig.f90:227-229).
+ *           eos: CDFGPU_EOS_*; pref: -r value (ignored for NEUTRAL).
+ *           j_first_global / ny_global: when the caller hands over a latitude band, the 0-based global index of
+ *           the band's first row and the global row count, so that the reference's skipping of the first and
+ *           last global row (cdfmocsig.f90:405-407) is reproduced; pass 0 and ny for the whole domain.
+ * submit  enqueues record jt: raw file values of zv, zt, zs (nx,ny,nz-1); the missing-value scrub
+ *           (cdfmocsig.f90:375,383-384), optional bolus velocity (zveiv, -eiv, :376-379), area, EOS, bin and
+ *           scatter-add are fused in one kernel.
+ * fetch   dmoc(nb,nbins,ny) in Sv, integrated from the densest bin (cdfmocsig.f90:471-475).
+ * bins_device: diagnostic for parity tests -- the bin index (1..nbins) of every cell of a device-resident
+ *           record, computed by the same device function the fused kernel uses. */
+int cdfmocsig_gpu_setup(int nx, int ny, int nz, int nb, int nbins, float sigmin, float sigstp, float pref, int eos,
+                        const float *e1v, const float *e3v, const int16_t *ibmask, float zspv, float zspt, float zsps,
+                        int j_first_global, int ny_global);
+int cdfmocsig_gpu_submit(int slot, int jt, const float *zv, const float *zt, const float *zs, const float *zveiv,
+                         const float *e3v_vvl);
+int cdfmocsig_gpu_fetch(int slot, double *dmoc);
+int cdfmocsig_gpu_compute_device(const float *d_zv, const float *d_zt, const float *d_zs, const float *d_zveiv,
+                                 const float *d_e3v_vvl, double *d_dmoc, void *stream);
+int cdfmocsig_gpu_bins_device(const float *d_zt, const float *d_zs, int32_t *d_ibin, void *stream);
+int cdfmocsig_gpu_kernel_ms(int slot, float *ms);
+int cdfmocsig_gpu_teardown(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDFGPU_H */
