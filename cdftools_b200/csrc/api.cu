@@ -41,8 +41,8 @@ static int make_ws(Workspace &w, int ny)
 {
     CDF_CUDA(cudaMalloc(&w.d_tickets, 2 * sizeof(int)));
     CDF_CUDA(cudaMalloc(&w.d_col, (size_t)ny * sizeof(int)));
-    CDF_CUDA(cudaMemset(w.d_tickets, 0, 2 * sizeof(int)));
-    CDF_CUDA(cudaMemset(w.d_col, 0, (size_t)ny * sizeof(int)));
+    CDF_CUDA(cudaMemsetAsync(w.d_tickets, 0, 2 * sizeof(int), g.s_compute));
+    CDF_CUDA(cudaMemsetAsync(w.d_col, 0, (size_t)ny * sizeof(int), g.s_compute));
     w.parity = 0;
     return CDFGPU_OK;
 }
@@ -328,10 +328,10 @@ int cdfmoc_gpu_setup(int nx, int ny, int nz, int nb, const float *e1v, const flo
     std::vector<uint32_t> words;
     const bool binary = pack_masks(nx, ny, nb, ibmask, moc.pitchw, words);
     moc.general = binary ? 0 : 1;
-    CDF_CUDA(cudaMemcpy(moc.d_maskw, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    CDF_CUDA(cudaMemcpy(moc.d_ibmask, ibmask, nxy * nb * sizeof(int16_t), cudaMemcpyHostToDevice));
-    CDF_CUDA(cudaMemcpy(moc.d_e1v, e1v, nxy * sizeof(float), cudaMemcpyHostToDevice));
-    CDF_CUDA(cudaMemcpy(moc.d_e3m, e3v, nxy * (size_t)(nz - 1) * sizeof(float), cudaMemcpyHostToDevice));
+    CDF_CUDA(cudaMemcpyAsync(moc.d_maskw, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, g.s_compute));
+    CDF_CUDA(cudaMemcpyAsync(moc.d_ibmask, ibmask, nxy * nb * sizeof(int16_t), cudaMemcpyHostToDevice, g.s_compute));
+    CDF_CUDA(cudaMemcpyAsync(moc.d_e1v, e1v, nxy * sizeof(float), cudaMemcpyHostToDevice, g.s_compute));
+    CDF_CUDA(cudaMemcpyAsync(moc.d_e3m, e3v, nxy * (size_t)(nz - 1) * sizeof(float), cudaMemcpyHostToDevice, g.s_compute));
     if ((rc = moc_build_area())) return rc;
     moc.smem = (size_t)(kMocThreads / 32) * (nz - 1) * nb * sizeof(double);
     moc.grid = 0;
@@ -340,6 +340,7 @@ int cdfmoc_gpu_setup(int nx, int ny, int nz, int nb, const float *e1v, const flo
         CDF_CUDA(cudaMalloc(&moc.slots[s].d_in[0], moc.in_elems() * sizeof(float) + 16));
         CDF_CUDA(cudaMalloc(&moc.slots[s].d_out, moc.out_elems() * sizeof(double)));
     }
+    CDF_CUDA(cudaStreamSynchronize(g.s_compute));  // setup copies are ordered on the compute stream; drain them
     moc.ready = true;
     return CDFGPU_OK;
 }
@@ -351,7 +352,7 @@ int cdfmoc_gpu_set_e3v(const float *e3v)
     REQUIRE(e3v, CDFGPU_ERR_ARG, "cdfmoc_gpu_set_e3v: null pointer");
     // the area field is read by every kernel in flight: drain first (rare path, once per record with -vvl)
     CDF_CUDA(cudaStreamSynchronize(g.s_compute));
-    CDF_CUDA(cudaMemcpy(moc.d_e3m, e3v, (size_t)moc.nx * moc.ny * (moc.nz - 1) * sizeof(float), cudaMemcpyHostToDevice));
+    CDF_CUDA(cudaMemcpyAsync(moc.d_e3m, e3v, (size_t)moc.nx * moc.ny * (moc.nz - 1) * sizeof(float), cudaMemcpyHostToDevice, g.s_compute));
     return moc_build_area();
 }
 

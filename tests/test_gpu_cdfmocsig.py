@@ -58,11 +58,12 @@ def test_cdfmocsig_bins_bit_exact_dense_sweep(gpu_lib, oracle_mod):
     t = rng.uniform(-2.5, 34.0, n).astype(np.float32).reshape(1, 1, n)
     s = rng.uniform(0.0, 42.0, n).astype(np.float32).reshape(1, 1, n)
     s[0, 0, ::13] = 0.0
-    m = synth.make_mesh((8, 1, 2))
-    ib = np.ones((1, 8, 1), np.int16)
+    e1v = np.ones((1, n), np.float32)          # a 1 x n x 2 "grid": one level of n cells is what bins_device walks
+    e3v = np.ones((2, 1, n), np.float32)
+    ib = np.ones((1, n, 1), np.int16)
     for pref, eos in ((0.0, 0), (1000.0, 0), (2000.0, 0), (0.0, 1), (2000.0, 1), (0.0, 2)):
         nbins, smin, sstp = oracle_mod.default_bins(pref, eos == 2)
-        gpu_lib.cdfmocsig_setup(m.e1v, m.e3v_0, ib, 2, nbins, smin, sstp, pref, eos)
+        gpu_lib.cdfmocsig_setup(e1v, e3v, ib, 2, nbins, smin, sstp, pref, eos)
         got = gpu_bins(gpu_lib, t, s)
         import oracle.np_oracle as npo
         ref, _, _ = npo.mocsig_bins(t, s, 0.0, pref, eos, smin, sstp, nbins)
