@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "moc_kernel.cuh"
+#include "moc_kernel_tma.cuh"
 #include "mocsig_kernel.cuh"
 
 namespace cdfgpu {
@@ -113,30 +114,114 @@ struct MocPlan {
     Slot slots[CDFGPU_MAX_SLOTS];
     int grid = 0;
     size_t smem = 0;
+    int variant = 0;       // register-staged kernel: unroll / occupancy variant ($CDFGPU_K1_VARIANT, experiments)
+    bool use_tma = false;  // $CDFGPU_K1=tma selects the TMA-fed class-sum kernel
+    // TMA path (0/1 masks, <= 8 distinct mask tuples, finite area)
+    uint8_t *d_classes = nullptr;
+    int nclass = 0, lane_cells = 0, ntile = 0, cpitch = 0, tma_warps = 0, tma_grid = 0, tma_chunk = 1;
+    size_t tma_smem = 0;
     size_t in_elems() const { return (size_t)(nz - 1) * ny * nx; }
     size_t out_elems() const { return (size_t)nz * ny * nb; }
 };
 static MocPlan moc;
 
-template <int NB>
-static int moc_launch_t(const MocParams &p, cudaStream_t st)
+// Distinct 0/1 mask tuples -> class index (0 = no basin); 4 pre-shifted byte planes, 255 outside the row.
+// Returns the number of classes, or 0 when the class path does not apply (non-binary masks, > 8 classes).
+static int pack_classes(int nx, int ny, int nb, const int16_t *ibmask, int cpitch, std::vector<uint8_t> &planes,
+                        uint32_t *class_bits)
 {
-    if (moc.grid == 0) {
-        int occ = 0;
-        CDF_CUDA(cudaFuncSetAttribute(moc_zonal_scan_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)moc.smem));
-        CDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, moc_zonal_scan_kernel<NB>, kMocThreads, moc.smem));
-        if (occ < 1) return set_error(CDFGPU_ERR_ARG, "cdfmoc: kernel does not fit (nz*nb too large for shared memory)");
-        moc.grid = occ * g.sm_count;
+    std::vector<uint8_t> cls((size_t)nx * ny);
+    int nclass = 1;
+    class_bits[0] = 0u;
+    for (size_t c = 0; c < (size_t)nx * ny; ++c) {
+        uint32_t bits = 0;
+        for (int b = 0; b < nb; ++b) {
+            const int16_t m = ibmask[c * nb + b];
+            if (m != 0 && m != 1) return 0;
+            if (m) bits |= 1u << b;
+        }
+        int q = 0;
+        while (q < nclass && class_bits[q] != bits) ++q;
+        if (q == nclass) {
+            if (nclass == kTmaMaxClasses) return 0;
+            class_bits[nclass++] = bits;
+        }
+        cls[c] = (uint8_t)q;
     }
-    moc_zonal_scan_kernel<NB><<<moc.grid, kMocThreads, moc.smem, st>>>(p);
+    planes.assign((size_t)4 * ny * cpitch, (uint8_t)255);
+    for (int s = 0; s < 4; ++s)
+        for (int j = 0; j < ny; ++j)
+            memcpy(planes.data() + ((size_t)s * ny + j) * cpitch + s, cls.data() + (size_t)j * nx, (size_t)nx);
+    return nclass;
+}
+
+template <int NB>
+static int moc_tma_launch_t(const MocTmaParams &p, cudaStream_t st)
+{
+    auto kern = moc_zonal_scan_tma_kernel<NB>;
+    if (moc.tma_grid == 0) {
+        int occ = 0;
+        CDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)moc.tma_smem));
+        CDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, moc.tma_warps * 32, moc.tma_smem));
+        if (occ < 1) return set_error(CDFGPU_ERR_ARG, "cdfmoc: TMA kernel does not fit in shared memory");
+        moc.tma_grid = occ * g.sm_count;
+    }
+    kern<<<moc.tma_grid, moc.tma_warps * 32, moc.tma_smem, st>>>(p);
     CDF_CUDA(cudaGetLastError());
     ++g.launches;
     return CDFGPU_OK;
 }
 
+template <int NB, int UNROLL, int MINB>
+static int moc_launch_v(const MocParams &p, cudaStream_t st)
+{
+    auto kern = moc_zonal_scan_kernel<NB, UNROLL, MINB>;
+    if (moc.grid == 0) {
+        int occ = 0;
+        CDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)moc.smem));
+        CDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kMocThreads, moc.smem));
+        if (occ < 1) return set_error(CDFGPU_ERR_ARG, "cdfmoc: kernel does not fit (nz*nb too large for shared memory)");
+        moc.grid = occ * g.sm_count;
+    }
+    kern<<<moc.grid, kMocThreads, moc.smem, st>>>(p);
+    CDF_CUDA(cudaGetLastError());
+    ++g.launches;
+    return CDFGPU_OK;
+}
+template <int NB>
+static int moc_launch_t(const MocParams &p, cudaStream_t st)
+{
+    switch (moc.variant) {
+    case 1: return moc_launch_v<NB, 4, 4>(p, st);
+    case 2: return moc_launch_v<NB, 2, 4>(p, st);
+    case 3: return moc_launch_v<NB, 8, 2>(p, st);
+    case 4: return moc_launch_v<NB, 6, 2>(p, st);
+    }
+    return moc_launch_v<NB, 4, 3>(p, st);
+}
+
 static int moc_launch(const float *d_zv, double *d_out, Workspace &ws, cudaStream_t st)
 {
+    if (!moc.general && moc.nclass > 0 && moc.use_tma) {  // TMA-fed class-sum kernel
+        MocTmaParams t;
+        t.zv = d_zv; t.area = moc.d_area; t.classes = moc.d_classes; t.ibmask = moc.d_ibmask; t.out = d_out;
+        t.tickets = ws.d_tickets; t.col_done = ws.d_col;
+        t.nx = moc.nx; t.ny = moc.ny; t.nz = moc.nz; t.nclass = moc.nclass;
+        t.lane_cells = moc.lane_cells; t.ntile = moc.ntile; t.cpitch = moc.cpitch;
+        t.parity = ws.parity; t.chunk = moc.tma_chunk; t.warps = moc.tma_warps;
+        ws.parity ^= 1;
+        switch (moc.nb) {
+        case 1: return moc_tma_launch_t<1>(t, st);
+        case 2: return moc_tma_launch_t<2>(t, st);
+        case 3: return moc_tma_launch_t<3>(t, st);
+        case 4: return moc_tma_launch_t<4>(t, st);
+        case 5: return moc_tma_launch_t<5>(t, st);
+        case 6: return moc_tma_launch_t<6>(t, st);
+        case 7: return moc_tma_launch_t<7>(t, st);
+        case 8: return moc_tma_launch_t<8>(t, st);
+        }
+        return set_error(CDFGPU_ERR_ARG, "cdfmoc: nb must be 1..8");
+    }
     MocParams p;
     p.zv = d_zv;
     p.area = moc.d_area;
@@ -297,7 +382,7 @@ int cdfmoc_gpu_teardown(void)
     if (!moc.ready && !moc.d_area) return CDFGPU_OK;
     if (g.inited) cdfgpu_synchronize();
     cudaFree(moc.d_e1v); cudaFree(moc.d_e3m); cudaFree(moc.d_area); cudaFree(moc.d_maskw);
-    cudaFree(moc.d_ibmask); cudaFree(moc.d_flag);
+    cudaFree(moc.d_ibmask); cudaFree(moc.d_flag); cudaFree(moc.d_classes);
     free_ws(moc.ws_int); free_ws(moc.ws_ext);
     for (auto &s : moc.slots) free_slot(s);
     moc = MocPlan();
@@ -313,6 +398,12 @@ int cdfmoc_gpu_setup(int nx, int ny, int nz, int nb, const float *e1v, const flo
     cdfmoc_gpu_teardown();
     moc.nx = nx; moc.ny = ny; moc.nz = nz; moc.nb = nb;
     moc.pitchw = (nx + 6) / 4 + 1;
+    {
+        const char *e = getenv("CDFGPU_K1");
+        moc.use_tma = e && !strcmp(e, "tma");
+        const char *v = getenv("CDFGPU_K1_VARIANT");
+        moc.variant = v ? atoi(v) : 0;
+    }
     // rows shorter than ~16 KB are handed out two levels at a time to halve the ticket traffic
     moc.chunk = (nx < 4096) ? 2 : 1;
     const size_t nxy = (size_t)nx * ny;
@@ -335,6 +426,35 @@ int cdfmoc_gpu_setup(int nx, int ny, int nz, int nb, const float *e1v, const flo
     if ((rc = moc_build_area())) return rc;
     moc.smem = (size_t)(kMocThreads / 32) * (nz - 1) * nb * sizeof(double);
     moc.grid = 0;
+    // ---- TMA path geometry: tiles of 32*L cells, L = 4 (mod 8) <= 60, ntile tiles per row
+    {
+        const int cells = nx + 3;  // worst-case shifted row length
+        moc.ntile = (cells + 32 * kTmaMaxLaneCells - 1) / (32 * kTmaMaxLaneCells);
+        int L = ((cells + moc.ntile - 1) / moc.ntile + 31) / 32;
+        L = ((L + 3) / 8) * 8 + 4;
+        if (L - 8 >= 4 && 32 * (L - 8) * moc.ntile >= cells) L -= 8;
+        moc.lane_cells = L;
+        moc.cpitch = moc.ntile * 32 * L;
+        uint32_t class_bits[kTmaMaxClasses] = {0};
+        std::vector<uint8_t> planes;
+        moc.nclass = (binary && moc.use_tma) ? pack_classes(nx, ny, nb, ibmask, moc.cpitch, planes, class_bits) : 0;
+        const size_t per_warp = ((size_t)kTmaStages * 32 * L * 9 + (size_t)kTmaMaxClasses * 32 * 8 +
+                                 (size_t)(nz - 1) * nb * 8 + 64 + 127) & ~(size_t)127;
+        moc.tma_warps = (int)std::min<size_t>(8, (220 * 1024) / per_warp);
+        if (moc.tma_warps < 1) moc.nclass = 0;  // nz*nb too large for the per-warp scan buffer: register kernel
+        if (moc.nclass > 0) {
+            moc.tma_smem = per_warp * moc.tma_warps;
+            moc.tma_grid = 0;
+            const long warps_total = (long)g.sm_count * moc.tma_warps;
+            long chunk = ((long)ny * (nz - 1)) / (warps_total * 20);
+            moc.tma_chunk = (int)std::max<long>(1, std::min<long>(chunk, 8));
+            CDF_CUDA(cudaMalloc(&moc.d_classes, planes.size() + 16));
+            CDF_CUDA(cudaMemcpyAsync(moc.d_classes, planes.data(), planes.size(), cudaMemcpyHostToDevice, g.s_compute));
+            CDF_CUDA(cudaMemcpyToSymbolAsync(c_class_bits, class_bits, sizeof(class_bits), 0, cudaMemcpyHostToDevice,
+                                             g.s_compute));
+            CDF_CUDA(cudaStreamSynchronize(g.s_compute));
+        }
+    }
     for (int s = 0; s < g.nslots; ++s) {
         if ((rc = make_slot_events(moc.slots[s]))) return rc;
         CDF_CUDA(cudaMalloc(&moc.slots[s].d_in[0], moc.in_elems() * sizeof(float) + 16));

@@ -38,21 +38,41 @@ struct MocParams {
 };
 
 constexpr int kMocThreads = 256;
-constexpr int kMocUnroll = 4;
 
-template <int NB>
-__device__ __forceinline__ void moc_cell(float a, float v, uint32_t mbits, double (&acc)[NB], float &badf)
+// acc -= dp when bit `BIT` of mbits is set, as ONE predicated DADD (the compiler's own lowering of the C++
+// conditional is an unconditional DADD plus two FSELs per basin, which made FSEL 37% of all issued instructions).
+template <int BIT>
+__device__ __forceinline__ void sub_if_bit(double &acc, double dp, uint32_t mbits)
+{
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 t;\n\t"
+        "and.b32 t, %2, %3;\n\t"
+        "setp.ne.b32 p, t, 0;\n\t"
+        "@p sub.rn.f64 %0, %0, %1;\n\t"
+        "}"
+        : "+d"(acc)
+        : "d"(dp), "r"(mbits), "n"(1u << BIT));
+}
+
+template <int NB, int SHIFT>
+__device__ __forceinline__ void moc_cell(float a, float v, uint32_t mword, double (&acc)[NB], float &badf)
 {
     const float p = __fmul_rn(a, v);
     badf = __fmaf_rn(p, 0.0f, badf);  // NaN iff p is NaN/Inf, else unchanged
     const double dp = (double)p;
-#pragma unroll
-    for (int b = 0; b < NB; ++b)
-        if (mbits & (1u << b)) acc[b] -= dp;
+    if (NB > 0) sub_if_bit<SHIFT + 0>(acc[0], dp, mword);
+    if (NB > 1) sub_if_bit<SHIFT + 1>(acc[NB > 1 ? 1 : 0], dp, mword);
+    if (NB > 2) sub_if_bit<SHIFT + 2>(acc[NB > 2 ? 2 : 0], dp, mword);
+    if (NB > 3) sub_if_bit<SHIFT + 3>(acc[NB > 3 ? 3 : 0], dp, mword);
+    if (NB > 4) sub_if_bit<SHIFT + 4>(acc[NB > 4 ? 4 : 0], dp, mword);
+    if (NB > 5) sub_if_bit<SHIFT + 5>(acc[NB > 5 ? 5 : 0], dp, mword);
+    if (NB > 6) sub_if_bit<SHIFT + 6>(acc[NB > 6 ? 6 : 0], dp, mword);
+    if (NB > 7) sub_if_bit<SHIFT + 7>(acc[NB > 7 ? 7 : 0], dp, mword);
 }
 
 // Fast path: exact for 0/1 masks and finite products.  Returns lane partial sums.
-template <int NB>
+template <int NB, int kMocUnroll>
 __device__ __forceinline__ void row_sums_fast(const MocParams &p, int j, int k, int lane, uint64_t pol,
                                               double (&acc)[NB], float &badf)
 {
@@ -82,10 +102,10 @@ __device__ __forceinline__ void row_sums_fast(const MocParams &p, int j, int k, 
         }
 #pragma unroll
         for (int u = 0; u < kMocUnroll; ++u) {
-            moc_cell<NB>(aa[u].x, vv[u].x, mm[u], acc, badf);
-            moc_cell<NB>(aa[u].y, vv[u].y, mm[u] >> 8, acc, badf);
-            moc_cell<NB>(aa[u].z, vv[u].z, mm[u] >> 16, acc, badf);
-            moc_cell<NB>(aa[u].w, vv[u].w, mm[u] >> 24, acc, badf);
+            moc_cell<NB, 0>(aa[u].x, vv[u].x, mm[u], acc, badf);
+            moc_cell<NB, 8>(aa[u].y, vv[u].y, mm[u], acc, badf);
+            moc_cell<NB, 16>(aa[u].z, vv[u].z, mm[u], acc, badf);
+            moc_cell<NB, 24>(aa[u].w, vv[u].w, mm[u], acc, badf);
         }
     }
 }
@@ -117,8 +137,8 @@ __device__ __noinline__ void row_general_store(const MocParams &p, int j, int k,
     }
 }
 
-template <int NB>
-__global__ void __launch_bounds__(kMocThreads, 3) moc_zonal_scan_kernel(const MocParams p)
+template <int NB, int UNROLL, int MINB>
+__global__ void __launch_bounds__(kMocThreads, MINB) moc_zonal_scan_kernel(const MocParams p)
 {
     extern __shared__ double s_scan[];  // [warps][(nz-1)*NB]
     const int lane = lane_id();
@@ -146,7 +166,7 @@ __global__ void __launch_bounds__(kMocThreads, 3) moc_zonal_scan_kernel(const Mo
             bool bad = p.general != 0;
             if (!bad) {
                 float badf = 0.0f;
-                row_sums_fast<NB>(p, j, k, lane, pol, acc, badf);
+                row_sums_fast<NB, UNROLL>(p, j, k, lane, pol, acc, badf);
                 bad = __any_sync(kFull, badf != badf);
             }
             if (bad) {

@@ -9,13 +9,12 @@
 //   H(b,ibin,j) += (0.d0 - dble(p)) * ibmask(b,i,j)                                    (:420, :439)
 // then  psi(b,nbins,j)=H/1e6 ; psi(b,bin,j) = psi(b,bin+1,j) + H(b,bin,j)/1e6           (:471-475)
 //
-// Design: one CTA per latitude row j (all levels), persistent grid of one CTA per SM fed by a ticket.  The
-// (level, 16-byte vector) pairs of the row are dealt round-robin to the CTA's threads, so the work is balanced to
-// one vector.  The basin masks are folded at setup into ONE byte per (j,i): the index of the distinct mask tuple
+// Design: one CTA (16 warps) per latitude row j (all levels), persistent grid of one CTA per SM fed by a ticket.
+// The row's (level, 256-cell window) pairs are dealt round-robin to the CTA's warps.  The basin masks are folded at setup into ONE byte per (j,i): the index of the distinct mask tuple
 // ("pattern") at that cell, 0 = no basin, 255 = cell excluded (i=1, i=nx, outside the row).  A cell therefore
-// costs ONE fp64 add into a shared-memory histogram hist[bin][pattern]; runs of equal (bin,pattern) along i are
-// first merged with a segmented warp scan so that smooth fields issue one shared atomic per run.  Cells with
-// pattern 0 or p == 0 contribute exactly nothing in the reference and skip the EOS altogether.
+// costs at most ONE fp64 add into a warp-private shared-memory histogram hist[bin][pattern] (no atomics, bitwise
+// reproducible); a lane owns 8 consecutive cells and merges equal (bin,pattern) neighbours in registers first.
+// Cells with pattern 0 or p == 0 contribute exactly nothing in the reference and skip the EOS altogether.
 // Epilogue per row: patterns -> basins, /1e6, cumulative sum from the densest bin, coalesced store.
 //
 // Bit-exactness of the bins: eos_sigma_exact() evaluates the reference expression with __dmul_rn/__dadd_rn only
@@ -26,8 +25,10 @@
 
 namespace cdfgpu {
 
-constexpr int kSigThreads = 1024;
+constexpr int kSigWarps = 16;
+constexpr int kSigThreads = kSigWarps * 32;
 constexpr int kSigMaxPat = 32;
+constexpr int kSigWinVec = 64;  // one warp step = 64 float4 vectors = 256 cells, 8 consecutive cells per lane
 
 struct EosConst {
     double c[CDF_EOS_NCOEF];
@@ -44,7 +45,7 @@ struct SigParams {
     const uint32_t *__restrict__ patw;                                 // [4][ny][pitchw] pattern bytes, shifted copies
     double *__restrict__ out;                                          // (ny, nbins, nb)
     int *tickets;                                                      // [2]
-    int nx, ny, nz, nb, nbins, npat, pitchw;
+    int nx, ny, nz, nb, nbins, npat, npat1, pitchw;  // npat incl. the all-zero pattern; npat1 = max(npat-1,1)
     int parity;
     int j_first_global, ny_global;
     int eos;  // CDFGPU_EOS_*
@@ -146,31 +147,54 @@ __device__ __forceinline__ int sigma_bin(float tem, float sal, const SigParams &
 __device__ __forceinline__ float scrub(float x, float spval) { return (x == spval) ? 0.0f : x; }
 
 // ---- histogram accumulation ---------------------------------------------------------------------------------
-// One item per lane: key (>=0: bin*kSigMaxPat+pattern, <0: nothing), val.  Runs of equal keys over adjacent lanes
-// are summed with a segmented scan; the last lane of each run issues one shared-memory atomic.
-__device__ __forceinline__ void hist_add_runs(double *hist, int key, double val, int lane)
+// Every warp owns a private histogram hist[(bin-1)*P + (pattern-1)] in shared memory, so no atomics are needed and
+// the result is bitwise reproducible.  A lane owns 8 CONSECUTIVE cells per step; equal (bin,pattern) neighbours are
+// merged in registers first (run-length), then the surviving entries of the 32 lanes are combined:
+//   * all live lanes share one key (smooth fields): one shuffle-tree sum, one read-modify-write;
+//   * otherwise __match_any groups the lanes by key: groups of >= 4 lanes are summed with a shuffle tree each,
+//     the remaining small groups write in <= 3 conflict-free rounds ordered by rank.
+__device__ __forceinline__ void hist_flush(double *hist, int key, double val, int lane)
 {
-    const int prev = __shfl_up_sync(kFull, key, 1);
-    const unsigned heads = __ballot_sync(kFull, lane == 0 || key != prev || key < 0);
-    const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const double o = __shfl_up_sync(kFull, val, d);
-        if (lane - d >= start) val += o;
+    const bool live = key >= 0;
+    const unsigned act = __ballot_sync(kFull, live);
+    if (act == 0u) return;  // warp-uniform
+    const int first = __ffs(act) - 1;
+    const int k0 = __shfl_sync(kFull, key, first);
+    if (__ballot_sync(kFull, live && key != k0) == 0u) {
+        const double t = warp_sum(live ? val : 0.0);
+        if (lane == first) hist[k0] += t;
+        __syncwarp();
+        return;
     }
-    const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
-    if (tail && key >= 0) atomicAdd(hist + key, val);
+    const unsigned peers = __match_any_sync(kFull, key);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    const bool big = live && __popc(peers) >= 4;
+    unsigned leaders = __ballot_sync(kFull, big && rank == 0);
+    while (leaders) {
+        const int L = __ffs(leaders) - 1;
+        leaders &= leaders - 1u;
+        const int kk = __shfl_sync(kFull, key, L);
+        const double t = warp_sum((live && key == kk) ? val : 0.0);
+        if (lane == L) hist[kk] += t;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const bool mine = live && !big && rank == r;
+        if (__any_sync(kFull, mine)) {
+            if (mine) hist[key] += val;
+            __syncwarp();
+        }
+    }
 }
 
+// One cell: (bin,pattern) key and fp64 contribution, or key = -1 when the cell contributes exactly nothing.
 template <int EOS, bool SIGMA0>
-__device__ __forceinline__ void sig_cell(const SigParams &p, float v, float ve, float t, float s, float a, uint32_t pat,
-                                         int &key, double &val, unsigned *s_poison)
+__device__ __forceinline__ void sig_cell(const SigParams &p, float pr, float t, float s, uint32_t pat, int &key,
+                                         double &val, unsigned *s_poison)
 {
     key = -1;
     val = 0.0;
-    v = scrub(v, p.spv);
-    if (p.zveiv) v = __fadd_rn(v, ve);
-    const float pr = __fmul_rn(v, a);
     if (pat == 255u || pr == 0.0f) return;         // excluded cell, or an exact zero contribution
     const bool finite = (__float_as_uint(pr) & 0x7f800000u) != 0x7f800000u;
     if (pat == 0u && finite) return;               // no basin covers the cell: (0-p)*0 == 0
@@ -186,31 +210,44 @@ __device__ __forceinline__ void sig_cell(const SigParams &p, float v, float ve, 
         if (bits) atomicOr(s_poison + (ib - 1), bits);
         if (pr != pr || pat == 0u) return;  // an Inf with a covering basin still accumulates below
     }
-    key = (ib - 1) * kSigMaxPat + (int)pat;
+    key = (ib - 1) * p.npat1 + (int)pat - 1;
     val = 0.0 - (double)pr;
+}
+
+// transport of one cell in fp32, exactly as the reference forms it: scrub, optional bolus velocity, zv*zarea
+__device__ __forceinline__ float sig_transport(const SigParams &p, float v, float ve, float a)
+{
+    v = scrub(v, p.spv);
+    if (p.zveiv) v = __fadd_rn(v, ve);
+    return __fmul_rn(v, a);
 }
 
 template <int EOS, bool SIGMA0>
 __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(const SigParams p)
 {
     extern __shared__ double s_mem[];
-    double *hist = s_mem;                                           // [nbins][kSigMaxPat]
-    double *comb = hist + (size_t)p.nbins * kSigMaxPat;             // [nbins][nb]
-    unsigned *s_poison = reinterpret_cast<unsigned *>(comb + (size_t)p.nbins * p.nb);  // [nbins]
+    const int hsize = p.nbins * p.npat1;                            // one private histogram
+    double *hist_all = s_mem;                                       // [kSigWarps][nbins][npat1]
+    double *comb = hist_all + (size_t)kSigWarps * hsize;            // [nbins][nb]
+    float *stage_all = reinterpret_cast<float *>(comb + (size_t)p.nbins * p.nb);  // [kSigWarps][3][8][32] p,t,s
+    unsigned *s_poison = reinterpret_cast<unsigned *>(stage_all + (size_t)kSigWarps * 3 * 8 * 32);  // [nbins]
     __shared__ int s_ticket[2];
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nzm1 = p.nz - 1;
     const uint64_t pol = make_evict_first_policy();
-    const int NV = (p.nx + 6) >> 2;  // vectors per row, upper bound over the 4 alignments
+    double *hist = hist_all + (size_t)warp * hsize;
+    float *st_p = stage_all + (size_t)warp * 3 * 8 * 32, *st_t = st_p + 8 * 32, *st_s = st_t + 8 * 32;
+    const int NV = (p.nx + 6) >> 2;                 // vectors per row, upper bound over the 4 alignments
+    const int wpr = (NV + kSigWinVec - 1) / kSigWinVec;  // windows per (level) row
+    const int total = nzm1 * wpr;                   // windows of one latitude row j
     int *ticket = p.tickets + p.parity;
     if (blockIdx.x == 0 && tid == 0) p.tickets[p.parity ^ 1] = 0;
 
     if (tid == 0) s_ticket[0] = atomicAdd(ticket, 1);
     int tsel = 0;
-    const int total = nzm1 * NV;  // (level, vector) pairs of one latitude row
     for (;;) {
-        for (int t = tid; t < p.nbins * kSigMaxPat; t += kSigThreads) hist[t] = 0.0;
+        for (int t = tid; t < kSigWarps * hsize; t += kSigThreads) hist_all[t] = 0.0;
         for (int t = tid; t < p.nbins; t += kSigThreads) s_poison[t] = 0u;
         __syncthreads();
         const int j = s_ticket[tsel];
@@ -221,55 +258,91 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
         const bool skip_row = (p.ny_global > 1) && (jg == 0 || jg == p.ny_global - 1);  // jj = 2..npjglo-1 only
 
         if (!skip_row) {
-            int k = 0, vi = tid;
-            while (vi >= NV) { vi -= NV; ++k; }
-            // warp-uniform trip count: lanes past the end idle through the collectives
-            for (int t = tid; t - lane < total; t += kSigThreads) {
-                int key[4] = {-1, -1, -1, -1};
-                double val[4] = {0.0, 0.0, 0.0, 0.0};
-                if (t < total) {
-                    const size_t e0 = ((size_t)k * p.ny + j) * (size_t)p.nx;
-                    const int s = (int)(e0 & 3);
-                    const int nvec = (s + p.nx + 3) >> 2;
-                    if (vi < nvec) {
-                        const size_t off = (e0 - s) + 4 * (size_t)vi;
-                        const uint32_t pw = __ldg(p.patw + ((size_t)s * p.ny + j) * p.pitchw + vi);
-                        if (pw != 0xffffffffu) {
-                            const float4 v4 = ld_stream_f4(reinterpret_cast<const float4 *>(p.zv + off), pol);
-                            const float4 a4 = ld_stream_f4(reinterpret_cast<const float4 *>(p.area + off), pol);
-                            const float4 t4 = ld_stream_f4(reinterpret_cast<const float4 *>(p.zt + off), pol);
-                            const float4 s4 = ld_stream_f4(reinterpret_cast<const float4 *>(p.zs + off), pol);
-                            float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (p.zveiv) e4 = ld_stream_f4(reinterpret_cast<const float4 *>(p.zveiv + off), pol);
-                            sig_cell<EOS, SIGMA0>(p, v4.x, e4.x, t4.x, s4.x, a4.x, pw & 255u, key[0], val[0], s_poison);
-                            sig_cell<EOS, SIGMA0>(p, v4.y, e4.y, t4.y, s4.y, a4.y, (pw >> 8) & 255u, key[1], val[1], s_poison);
-                            sig_cell<EOS, SIGMA0>(p, v4.z, e4.z, t4.z, s4.z, a4.z, (pw >> 16) & 255u, key[2], val[2], s_poison);
-                            sig_cell<EOS, SIGMA0>(p, v4.w, e4.w, t4.w, s4.w, a4.w, pw >> 24, key[3], val[3], s_poison);
+            int k = 0, win = warp;
+            while (win >= wpr) { win -= wpr; ++k; }
+            for (int w = warp; w < total; w += kSigWarps) {   // warp-uniform loop: one window of 64 vectors per trip
+                const size_t e0 = ((size_t)k * p.ny + j) * (size_t)p.nx;
+                const int s = (int)(e0 & 3);
+                const int nvec = (s + p.nx + 3) >> 2;
+                const int v0 = win * kSigWinVec + 2 * lane;   // this lane's two consecutive vectors = 8 cells
+                uint32_t pw0 = 0xffffffffu, pw1 = 0xffffffffu;
+                bool work = false;
+                if (v0 < nvec) {
+                    const size_t off = (e0 - s) + 4 * (size_t)v0;
+                    const uint32_t *pwp = p.patw + ((size_t)s * p.ny + j) * p.pitchw + v0;
+                    const bool two = v0 + 1 < nvec;
+                    pw0 = __ldg(pwp);
+                    if (two) pw1 = __ldg(pwp + 1);
+                    if ((pw0 & pw1) != 0xffffffffu) {
+                        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 *pv = reinterpret_cast<const float4 *>(p.zv + off);
+                        const float4 *pa = reinterpret_cast<const float4 *>(p.area + off);
+                        const float4 *pt = reinterpret_cast<const float4 *>(p.zt + off);
+                        const float4 *ps = reinterpret_cast<const float4 *>(p.zs + off);
+                        const float4 va = ld_stream_f4(pv, pol), vb = two ? ld_stream_f4(pv + 1, pol) : z4;
+                        const float4 aa = ld_stream_f4(pa, pol), ab = two ? ld_stream_f4(pa + 1, pol) : z4;
+                        const float4 ta = ld_stream_f4(pt, pol), tb = two ? ld_stream_f4(pt + 1, pol) : z4;
+                        const float4 sa = ld_stream_f4(ps, pol), sb = two ? ld_stream_f4(ps + 1, pol) : z4;
+                        float4 ea = z4, eb = z4;
+                        if (p.zveiv) {
+                            const float4 *pe = reinterpret_cast<const float4 *>(p.zveiv + off);
+                            ea = ld_stream_f4(pe, pol);
+                            if (two) eb = ld_stream_f4(pe + 1, pol);
+                        }
+                        float pr[8];
+                        pr[0] = sig_transport(p, va.x, ea.x, aa.x); pr[1] = sig_transport(p, va.y, ea.y, aa.y);
+                        pr[2] = sig_transport(p, va.z, ea.z, aa.z); pr[3] = sig_transport(p, va.w, ea.w, aa.w);
+                        pr[4] = sig_transport(p, vb.x, eb.x, ab.x); pr[5] = sig_transport(p, vb.y, eb.y, ab.y);
+                        pr[6] = sig_transport(p, vb.z, eb.z, ab.z); pr[7] = sig_transport(p, vb.w, eb.w, ab.w);
+                        const float tt[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+                        const float ss[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const uint32_t pat = ((c < 4 ? pw0 : pw1) >> (8 * (c & 3))) & 255u;
+                            work = work || (pat != 255u && pr[c] != 0.0f);
+                            st_p[c * 32 + lane] = pr[c];
+                            st_t[c * 32 + lane] = tt[c];
+                            st_s[c * 32 + lane] = ss[c];
                         }
                     }
                 }
-                if (__any_sync(kFull, (key[0] & key[1] & key[2] & key[3]) >= 0)) {
-                    // merge the lane's own 4 cells when they share a key (the common case in smooth fields)
-                    const bool same = key[0] == key[1] && key[1] == key[2] && key[2] == key[3];
-                    if (__all_sync(kFull, same)) {
-                        hist_add_runs(hist, key[0], (val[0] + val[1]) + (val[2] + val[3]), lane);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) hist_add_runs(hist, key[c], val[c], lane);
+                // Walk the lane's 8 consecutive cells (one copy of the EOS code): equal (bin,pattern) neighbours are
+                // merged in registers; a run is flushed to the warp's histogram when it ends.
+                if (__any_sync(kFull, work)) {
+                    int rkey = -1;
+                    double rval = 0.0;
+#pragma unroll 1
+                    for (int c = 0; c < 8; ++c) {
+                        int key = -1;
+                        double val = 0.0;
+                        if (work) {
+                            const uint32_t pat = ((c < 4 ? pw0 : pw1) >> (8 * (c & 3))) & 255u;
+                            sig_cell<EOS, SIGMA0>(p, st_p[c * 32 + lane], st_t[c * 32 + lane], st_s[c * 32 + lane], pat,
+                                                  key, val, s_poison);
+                        }
+                        const bool same = (key == rkey);
+                        hist_flush(hist, same ? -1 : rkey, rval, lane);   // collective; no-op unless some run ended
+                        rval = same ? rval + val : val;
+                        rkey = key;
                     }
+                    hist_flush(hist, rkey, rval, lane);
                 }
-                vi += kSigThreads;
-                while (vi >= NV) { vi -= NV; ++k; }
+                win += kSigWarps;
+                while (win >= wpr) { win -= wpr; ++k; }
             }
         }
         __syncthreads();
-        // patterns -> basins, /1e6 (dmoc/1.e6), poison handling
+        // private histograms -> one (fixed order: deterministic), patterns -> basins, /1e6, poison handling
         for (int t = tid; t < p.nbins * p.nb; t += kSigThreads) {
             const int bin = t / p.nb, b = t - bin * p.nb;
             double h = 0.0;
             for (int q = 1; q < p.npat; ++q) {
-                const double w = c_patw[q][b];
-                if (w != 0.0) h += hist[bin * kSigMaxPat + q] * w;
+                const double wgt = c_patw[q][b];
+                if (wgt != 0.0) {
+                    double hq = 0.0;
+                    for (int w = 0; w < kSigWarps; ++w) hq += hist_all[(size_t)w * hsize + bin * p.npat1 + q - 1];
+                    h += hq * wgt;
+                }
             }
             if ((s_poison[bin] >> b) & 1u) h = __longlong_as_double(0x7ff8000000000000LL);  // NaN transport
             comb[t] = h / 1.0e6;
