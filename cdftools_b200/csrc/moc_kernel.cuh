@@ -39,20 +39,15 @@ struct MocParams {
 
 constexpr int kMocThreads = 256;
 
-// acc -= dp when bit `BIT` of mbits is set, as ONE predicated DADD (the compiler's own lowering of the C++
-// conditional is an unconditional DADD plus two FSELs per basin, which made FSEL 37% of all issued instructions).
+// acc -= dp when bit `BIT` of mbits is set.  Written as ONE fused multiply-add with a multiplier of -1.0 or -0.0
+// built from the mask bit (only the high word differs): fma(dp,-1,acc) == acc - dp and fma(dp,-0,acc) == acc, both
+// exactly.  The plain C++ conditional (and a predicated PTX sub) is lowered by ptxas to an unconditional DADD plus
+// two FSELs per basin, which made FSEL 37% of all issued instructions (profiles/r01_k1v1_opmix.txt).
 template <int BIT>
 __device__ __forceinline__ void sub_if_bit(double &acc, double dp, uint32_t mbits)
 {
-    asm("{\n\t"
-        ".reg .pred p;\n\t"
-        ".reg .b32 t;\n\t"
-        "and.b32 t, %2, %3;\n\t"
-        "setp.ne.b32 p, t, 0;\n\t"
-        "@p sub.rn.f64 %0, %0, %1;\n\t"
-        "}"
-        : "+d"(acc)
-        : "d"(dp), "r"(mbits), "n"(1u << BIT));
+    const int hi = (mbits & (1u << BIT)) ? (int)0xBFF00000 : (int)0x80000000;
+    acc = fma(dp, __hiloint2double(hi, 0), acc);
 }
 
 template <int NB, int SHIFT>

@@ -52,6 +52,7 @@ struct SigParams {
     float sigmin, sigstp, pref;
     float spv, spt, sps;
     double dlh, dlref;
+    double inv_sigstp, qmargin;  // fast bin filter: 1/sigstp and the safety distance to a bin edge (q units); <0: off
 };
 
 // ---- equation of state ----------------------------------------------------------------------------------------
@@ -144,6 +145,60 @@ __device__ __forceinline__ int sigma_bin(float tem, float sal, const SigParams &
     return ib;
 }
 
+// ---- fast bin: FMA-evaluated polynomial + distance-to-bin-edge guard ------------------------------------------
+// The bin index is a monotone step function of sigma.  sigma is evaluated here with fused multiply-adds (half the
+// fp64 instructions of the reference's mul/add chain, more ILP); the result differs from the reference value by
+// rounding only.  q = (sigma - sigmin)/sigstp is formed in fp64 and compared with the nearest integer: when it is
+// farther than `qmargin` (set up on the host from the fp32 roundings of the reference's own bin formula plus a
+// generous bound on the evaluation difference, see api_mocsig.inc) the truncation is provably the reference's bin;
+// otherwise (about 1e-4 of the cells) the cell is re-evaluated with the exact chain.  Bit-exactness is kept.
+#define FM(a, b, c) fma((a), (b), (c))
+__device__ __forceinline__ double eos_dlr0_fma(double t, double s)
+{
+    const double q6 = CE(0, 6, 0);
+    const double q5 = FM(CE(1, 5, 0), s, CE(0, 5, 0));
+    const double q4 = FM(FM(CE(2, 4, 0), s, CE(1, 4, 0)), s, CE(0, 4, 0));
+    const double q3 = FM(FM(FM(CE(3, 3, 0), s, CE(2, 3, 0)), s, CE(1, 3, 0)), s, CE(0, 3, 0));
+    const double q2 = FM(FM(FM(FM(CE(4, 2, 0), s, CE(3, 2, 0)), s, CE(2, 2, 0)), s, CE(1, 2, 0)), s, CE(0, 2, 0));
+    const double q1 = FM(FM(FM(FM(FM(CE(5, 1, 0), s, CE(4, 1, 0)), s, CE(3, 1, 0)), s, CE(2, 1, 0)), s, CE(1, 1, 0)), s, CE(0, 1, 0));
+    const double q0 = FM(FM(FM(FM(FM(FM(CE(6, 0, 0), s, CE(5, 0, 0)), s, CE(4, 0, 0)), s, CE(3, 0, 0)), s, CE(2, 0, 0)), s, CE(1, 0, 0)), s, CE(0, 0, 0));
+    return FM(FM(FM(FM(FM(FM(q6, t, q5), t, q4), t, q3), t, q2), t, q1), t, q0);
+}
+__device__ __forceinline__ double eos_dlr123_fma(double t, double s, double h)
+{
+    const double a4 = CE(0, 4, 1);
+    const double a3 = FM(CE(1, 3, 1), s, CE(0, 3, 1));
+    const double a2 = FM(FM(CE(2, 2, 1), s, CE(1, 2, 1)), s, CE(0, 2, 1));
+    const double a1 = FM(FM(FM(CE(3, 1, 1), s, CE(2, 1, 1)), s, CE(1, 1, 1)), s, CE(0, 1, 1));
+    const double a0 = FM(FM(FM(FM(CE(4, 0, 1), s, CE(3, 0, 1)), s, CE(2, 0, 1)), s, CE(1, 0, 1)), s, CE(0, 0, 1));
+    const double r1 = FM(FM(FM(FM(a4, t, a3), t, a2), t, a1), t, a0);
+    const double b1 = FM(CE(1, 1, 2), s, CE(0, 1, 2));
+    const double b0 = FM(FM(CE(2, 0, 2), s, CE(1, 0, 2)), s, CE(0, 0, 2));
+    const double r2 = FM(FM(CE(0, 2, 2), t, b1), t, b0);
+    const double r3 = FM(CE(0, 1, 3), t, FM(CE(1, 0, 3), s, CE(0, 0, 3)));
+    return FM(FM(r3, h, r2), h, r1) * h;   // (dlr3*h + dlr2)*h + dlr1)*h, to be added to dlr0
+}
+
+template <int EOS, bool SIGMA0>
+__device__ __forceinline__ int sigma_bin_fast(float tem, float sal, const SigParams &p)
+{
+    if (EOS == CDFGPU_EOS_NEUTRAL || p.qmargin < 0.0) return sigma_bin<EOS, SIGMA0>(tem, sal, p);
+    const double t = DM((double)tem, 1.0 / 40.0);
+    const double s = __dsqrt_rn(DM(fabs(DA((double)sal, c_eos.rdeltaS)), c_eos.r1_S0));
+    double dlr = eos_dlr0_fma(t, s);
+    if (!SIGMA0) dlr += eos_dlr123_fma(t, s, p.dlh);
+    double sig = (dlr + p.dlref) - 1000.0;
+    if (sal == 0.0f || sal == p.sps) sig = 0.0;              // dltm / itmask
+    const double qa = (sig - (double)p.sigmin) * p.inv_sigstp;
+    if (fabs(qa) < 2.0e9) {                                   // false for NaN; INT() of huge values is the exact path's job
+        if (qa < 1.0 - p.qmargin) return 1;                   // INT(q) <= 0 -> MAX(ibin,1)
+        if (qa >= (double)p.nbins + p.qmargin) return p.nbins;   // MIN(ibin,nbins)
+        if (fabs(qa - rint(qa)) > p.qmargin) return min(max(__double2int_rz(qa), 1), p.nbins);
+    }
+    return sigma_bin<EOS, SIGMA0>(tem, sal, p);
+}
+#undef FM
+
 __device__ __forceinline__ float scrub(float x, float spval) { return (x == spval) ? 0.0f : x; }
 
 // ---- histogram accumulation ---------------------------------------------------------------------------------
@@ -153,7 +208,7 @@ __device__ __forceinline__ float scrub(float x, float spval) { return (x == spva
 //   * all live lanes share one key (smooth fields): one shuffle-tree sum, one read-modify-write;
 //   * otherwise __match_any groups the lanes by key: groups of >= 4 lanes are summed with a shuffle tree each,
 //     the remaining small groups write in <= 3 conflict-free rounds ordered by rank.
-__device__ __forceinline__ void hist_flush(double *hist, int key, double val, int lane)
+__device__ __noinline__ void hist_flush(double *hist, int key, double val, int lane)
 {
     const bool live = key >= 0;
     const unsigned act = __ballot_sync(kFull, live);
@@ -188,32 +243,6 @@ __device__ __forceinline__ void hist_flush(double *hist, int key, double val, in
     }
 }
 
-// One cell: (bin,pattern) key and fp64 contribution, or key = -1 when the cell contributes exactly nothing.
-template <int EOS, bool SIGMA0>
-__device__ __forceinline__ void sig_cell(const SigParams &p, float pr, float t, float s, uint32_t pat, int &key,
-                                         double &val, unsigned *s_poison)
-{
-    key = -1;
-    val = 0.0;
-    if (pat == 255u || pr == 0.0f) return;         // excluded cell, or an exact zero contribution
-    const bool finite = (__float_as_uint(pr) & 0x7f800000u) != 0x7f800000u;
-    if (pat == 0u && finite) return;               // no basin covers the cell: (0-p)*0 == 0
-    t = scrub(t, p.spt);
-    s = scrub(s, p.sps);
-    const int ib = sigma_bin<EOS, SIGMA0>(t, s, p);
-    if (!finite) {  // NaN/Inf transport: basin b is poisoned iff (0-p)*mask_b is NaN (NaN*x, or Inf*0)
-        unsigned bits = 0u;
-        for (int b = 0; b < p.nb; ++b) {
-            const double c = __dmul_rn(0.0 - (double)pr, c_patw[pat][b]);
-            if (c != c) bits |= 1u << b;
-        }
-        if (bits) atomicOr(s_poison + (ib - 1), bits);
-        if (pr != pr || pat == 0u) return;  // an Inf with a covering basin still accumulates below
-    }
-    key = (ib - 1) * p.npat1 + (int)pat - 1;
-    val = 0.0 - (double)pr;
-}
-
 // transport of one cell in fp32, exactly as the reference forms it: scrub, optional bolus velocity, zv*zarea
 __device__ __forceinline__ float sig_transport(const SigParams &p, float v, float ve, float a)
 {
@@ -222,22 +251,31 @@ __device__ __forceinline__ float sig_transport(const SigParams &p, float v, floa
     return __fmul_rn(v, a);
 }
 
+// per-warp staging area in shared memory (one 256-cell window)
+struct SigStage {
+    float ct[8 * 32];       // compacted scrubbed temperature of the cells that need a bin
+    float cs[8 * 32];       // compacted scrubbed salinity
+    uint16_t bin[8 * 32];   // bin of cell (c, lane), written by the dense EOS pass
+    uint8_t slot[8 * 32];   // compacted entry -> c*32+lane
+};
+
 template <int EOS, bool SIGMA0>
 __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(const SigParams p)
 {
     extern __shared__ double s_mem[];
+    const int nwarps = blockDim.x >> 5, nthreads = blockDim.x;     // chosen by the host so that shared memory fits
     const int hsize = p.nbins * p.npat1;                            // one private histogram
-    double *hist_all = s_mem;                                       // [kSigWarps][nbins][npat1]
-    double *comb = hist_all + (size_t)kSigWarps * hsize;            // [nbins][nb]
-    float *stage_all = reinterpret_cast<float *>(comb + (size_t)p.nbins * p.nb);  // [kSigWarps][3][8][32] p,t,s
-    unsigned *s_poison = reinterpret_cast<unsigned *>(stage_all + (size_t)kSigWarps * 3 * 8 * 32);  // [nbins]
+    double *hist_all = s_mem;                                       // [nwarps][nbins][npat1]
+    double *comb = hist_all + (size_t)nwarps * hsize;            // [nbins][nb]
+    SigStage *stage_all = reinterpret_cast<SigStage *>(comb + (((size_t)p.nbins * p.nb + 1) & ~(size_t)1));  // 16-B aligned
+    unsigned *s_poison = reinterpret_cast<unsigned *>(stage_all + nwarps);  // [nbins]
     __shared__ int s_ticket[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nzm1 = p.nz - 1;
     const uint64_t pol = make_evict_first_policy();
     double *hist = hist_all + (size_t)warp * hsize;
-    float *st_p = stage_all + (size_t)warp * 3 * 8 * 32, *st_t = st_p + 8 * 32, *st_s = st_t + 8 * 32;
+    SigStage &st = stage_all[warp];
     const int NV = (p.nx + 6) >> 2;                 // vectors per row, upper bound over the 4 alignments
     const int wpr = (NV + kSigWinVec - 1) / kSigWinVec;  // windows per (level) row
     const int total = nzm1 * wpr;                   // windows of one latitude row j
@@ -247,8 +285,8 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
     if (tid == 0) s_ticket[0] = atomicAdd(ticket, 1);
     int tsel = 0;
     for (;;) {
-        for (int t = tid; t < kSigWarps * hsize; t += kSigThreads) hist_all[t] = 0.0;
-        for (int t = tid; t < p.nbins; t += kSigThreads) s_poison[t] = 0u;
+        for (int t = tid; t < nwarps * hsize; t += nthreads) hist_all[t] = 0.0;
+        for (int t = tid; t < p.nbins; t += nthreads) s_poison[t] = 0u;
         __syncthreads();
         const int j = s_ticket[tsel];
         if (j >= p.ny) break;
@@ -260,13 +298,17 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
         if (!skip_row) {
             int k = 0, win = warp;
             while (win >= wpr) { win -= wpr; ++k; }
-            for (int w = warp; w < total; w += kSigWarps) {   // warp-uniform loop: one window of 64 vectors per trip
+            for (int w = warp; w < total; w += nwarps) {   // warp-uniform loop: one window of 64 vectors per trip
                 const size_t e0 = ((size_t)k * p.ny + j) * (size_t)p.nx;
                 const int s = (int)(e0 & 3);
                 const int nvec = (s + p.nx + 3) >> 2;
                 const int v0 = win * kSigWinVec + 2 * lane;   // this lane's two consecutive vectors = 8 cells
                 uint32_t pw0 = 0xffffffffu, pw1 = 0xffffffffu;
-                bool work = false;
+                unsigned need = 0u;                            // bit c: cell c needs a bin (contributes)
+                float tt[8], ss[8], pr[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) pr[c] = 0.0f;
+                // ---- phase A: load, transport, which cells contribute -----------------------------------------
                 if (v0 < nvec) {
                     const size_t off = (e0 - s) + 4 * (size_t)v0;
                     const uint32_t *pwp = p.patw + ((size_t)s * p.ny + j) * p.pitchw + v0;
@@ -289,58 +331,99 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
                             ea = ld_stream_f4(pe, pol);
                             if (two) eb = ld_stream_f4(pe + 1, pol);
                         }
-                        float pr[8];
                         pr[0] = sig_transport(p, va.x, ea.x, aa.x); pr[1] = sig_transport(p, va.y, ea.y, aa.y);
                         pr[2] = sig_transport(p, va.z, ea.z, aa.z); pr[3] = sig_transport(p, va.w, ea.w, aa.w);
                         pr[4] = sig_transport(p, vb.x, eb.x, ab.x); pr[5] = sig_transport(p, vb.y, eb.y, ab.y);
                         pr[6] = sig_transport(p, vb.z, eb.z, ab.z); pr[7] = sig_transport(p, vb.w, eb.w, ab.w);
-                        const float tt[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
-                        const float ss[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                        tt[0] = ta.x; tt[1] = ta.y; tt[2] = ta.z; tt[3] = ta.w; tt[4] = tb.x; tt[5] = tb.y; tt[6] = tb.z; tt[7] = tb.w;
+                        ss[0] = sa.x; ss[1] = sa.y; ss[2] = sa.z; ss[3] = sa.w; ss[4] = sb.x; ss[5] = sb.y; ss[6] = sb.z; ss[7] = sb.w;
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
                             const uint32_t pat = ((c < 4 ? pw0 : pw1) >> (8 * (c & 3))) & 255u;
-                            work = work || (pat != 255u && pr[c] != 0.0f);
-                            st_p[c * 32 + lane] = pr[c];
-                            st_t[c * 32 + lane] = tt[c];
-                            st_s[c * 32 + lane] = ss[c];
+                            const bool finite = (__float_as_uint(pr[c]) & 0x7f800000u) != 0x7f800000u;
+                            // excluded cell, exact zero, or finite transport not covered by any basin: contributes nothing
+                            if (pat != 255u && pr[c] != 0.0f && (pat != 0u || !finite)) need |= 1u << c;
                         }
                     }
                 }
-                // Walk the lane's 8 consecutive cells (one copy of the EOS code): equal (bin,pattern) neighbours are
-                // merged in registers; a run is flushed to the warp's histogram when it ends.
-                if (__any_sync(kFull, work)) {
-                    int rkey = -1;
-                    double rval = 0.0;
-#pragma unroll 1
+                // ---- compaction: the cells that need the EOS, in (lane, c) order, over the whole warp ------------
+                const int mine = __popc(need);
+                int base = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(kFull, base, d);
+                    if (lane >= d) base += o;
+                }
+                const int nneed = __shfl_sync(kFull, base, 31);
+                base -= mine;
+                if (nneed > 0) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (need & (1u << c)) {
+                            const int e = base + __popc(need & ((1u << c) - 1u));
+                            st.ct[e] = tt[c];
+                            st.cs[e] = ss[c];
+                            st.slot[e] = (uint8_t)(c * 32 + lane);
+                        }
+                    __syncwarp();
+                    // ---- phase B: dense EOS + bin over the compacted list ---------------------------------------
+                    for (int e = lane; e < nneed; e += 32)
+                        st.bin[st.slot[e]] =
+                            (uint16_t)sigma_bin_fast<EOS, SIGMA0>(scrub(st.ct[e], p.spt), scrub(st.cs[e], p.sps), p);
+                    __syncwarp();
+                    // ---- phase C: the lane's 8 consecutive cells, all in registers: key/value per cell, equal
+                    // (bin,pattern) neighbours merged (a run's sum travels to its last cell), then the surviving entries
+                    // are flushed to the warp's private histogram (hist_flush is a warp collective) ----------------
+                    int key[8];
+                    double val[8];
+#pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        int key = -1;
-                        double val = 0.0;
-                        if (work) {
+                        key[c] = -1;
+                        val[c] = 0.0;
+                        if (need & (1u << c)) {
                             const uint32_t pat = ((c < 4 ? pw0 : pw1) >> (8 * (c & 3))) & 255u;
-                            sig_cell<EOS, SIGMA0>(p, st_p[c * 32 + lane], st_t[c * 32 + lane], st_s[c * 32 + lane], pat,
-                                                  key, val, s_poison);
+                            const int ib = st.bin[c * 32 + lane];
+                            bool add = true;
+                            if ((__float_as_uint(pr[c]) & 0x7f800000u) == 0x7f800000u) {
+                                // NaN/Inf transport: basin b is poisoned iff (0-p)*mask_b is NaN (NaN*x, or Inf*0)
+                                unsigned bits = 0u;
+                                for (int b = 0; b < p.nb; ++b) {
+                                    const double cc = __dmul_rn(0.0 - (double)pr[c], c_patw[pat][b]);
+                                    if (cc != cc) bits |= 1u << b;
+                                }
+                                if (bits) atomicOr(s_poison + (ib - 1), bits);
+                                add = !(pr[c] != pr[c] || pat == 0u);  // an Inf with a covering basin still accumulates
+                            }
+                            if (add) {
+                                key[c] = (ib - 1) * p.npat1 + (int)pat - 1;
+                                val[c] = 0.0 - (double)pr[c];
+                            }
                         }
-                        const bool same = (key == rkey);
-                        hist_flush(hist, same ? -1 : rkey, rval, lane);   // collective; no-op unless some run ended
-                        rval = same ? rval + val : val;
-                        rkey = key;
                     }
-                    hist_flush(hist, rkey, rval, lane);
+#pragma unroll
+                    for (int c = 1; c < 8; ++c)
+                        if (key[c] == key[c - 1] && key[c] >= 0) {
+                            val[c] += val[c - 1];
+                            key[c - 1] = -1;
+                        }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (__any_sync(kFull, key[c] >= 0)) hist_flush(hist, key[c], val[c], lane);
                 }
-                win += kSigWarps;
+                win += nwarps;
                 while (win >= wpr) { win -= wpr; ++k; }
             }
         }
         __syncthreads();
         // private histograms -> one (fixed order: deterministic), patterns -> basins, /1e6, poison handling
-        for (int t = tid; t < p.nbins * p.nb; t += kSigThreads) {
+        for (int t = tid; t < p.nbins * p.nb; t += nthreads) {
             const int bin = t / p.nb, b = t - bin * p.nb;
             double h = 0.0;
             for (int q = 1; q < p.npat; ++q) {
                 const double wgt = c_patw[q][b];
                 if (wgt != 0.0) {
                     double hq = 0.0;
-                    for (int w = 0; w < kSigWarps; ++w) hq += hist_all[(size_t)w * hsize + bin * p.npat1 + q - 1];
+                    for (int w = 0; w < nwarps; ++w) hq += hist_all[(size_t)w * hsize + bin * p.npat1 + q - 1];
                     h += hq * wgt;
                 }
             }
@@ -357,7 +440,7 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
         }
         __syncthreads();
         double *o = p.out + (size_t)j * p.nbins * p.nb;
-        for (int t = tid; t < p.nbins * p.nb; t += kSigThreads) o[t] = comb[t];
+        for (int t = tid; t < p.nbins * p.nb; t += nthreads) o[t] = comb[t];
         __syncthreads();
     }
 }
@@ -367,7 +450,7 @@ template <int EOS, bool SIGMA0>
 __global__ void mocsig_bins_kernel(const SigParams p, int32_t *__restrict__ ibin, size_t n)
 {
     for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x)
-        ibin[c] = sigma_bin<EOS, SIGMA0>(scrub(p.zt[c], p.spt), scrub(p.zs[c], p.sps), p);
+        ibin[c] = sigma_bin_fast<EOS, SIGMA0>(scrub(p.zt[c], p.spt), scrub(p.zs[c], p.sps), p);
 }
 
 // setup kernel: area = fl32(e1v * e3v) (cdfmocsig.f90:390), e3v NOT masked.
