@@ -1,0 +1,157 @@
+MODULE cdfgpu
+  !!======================================================================
+  !!                     ***  MODULE  cdfgpu  ***
+  !! ISO_C_BINDING interface to libcdfgpu.so (include/cdfgpu.h): the B200
+  !! implementation of the cdfmoc / cdfmocsig hot loops.
+  !!
+  !! This is the thin bind(C) layer a CDFTOOLS maintainer adds to src/ so that
+  !!    src/cdfmoc.f90:352-388      ->  cdfmoc_gpu_submit / cdfmoc_gpu_fetch
+  !!    src/cdfmocsig.f90:366-475   ->  cdfmocsig_gpu_submit / cdfmocsig_gpu_fetch
+  !! The host program stays Fortran: same command line, same cdfio calls, same
+  !! output file.  INTEGRATION.md shows the call-site patches.
+  !!
+  !! NOTE: gfortran / netcdf-fortran are not available in the build image of this
+  !! repository, so this file is shipped as source and has NOT been compiled here.
+  !! It only uses standard Fortran 2003 interoperability features.
+  !!
+  !! Array conventions: Fortran arrays are passed as they are declared in the
+  !! reference (column-major), which is exactly the C [k][j][i] order the library
+  !! expects -- no transposes:
+  !!    e1v(npiglo,npjglo)  e3v(npiglo,npjglo,npk)  ibmask(nbasins,npiglo,npjglo)
+  !!    zv(npiglo,npjglo,npk-1)   dmoc(nbasins,npjglo,npk) / dmoc(nvaro,nbins,npjglo)
+  !!======================================================================
+  USE, INTRINSIC :: ISO_C_BINDING
+  IMPLICIT NONE
+  PUBLIC
+
+  INTEGER(C_INT), PARAMETER :: CDFGPU_OK = 0
+  INTEGER(C_INT), PARAMETER :: CDFGPU_EOS_EOS80 = 0, CDFGPU_EOS_TEOS10 = 1, CDFGPU_EOS_NEUTRAL = 2
+
+  INTERFACE
+     ! ---- lifecycle ---------------------------------------------------------
+     INTEGER(C_INT) FUNCTION cdfgpu_init(device, nslots) BIND(C, NAME='cdfgpu_init')
+       IMPORT :: C_INT
+       INTEGER(C_INT), VALUE :: device, nslots
+     END FUNCTION cdfgpu_init
+
+     INTEGER(C_INT) FUNCTION cdfgpu_finalize() BIND(C, NAME='cdfgpu_finalize')
+       IMPORT :: C_INT
+     END FUNCTION cdfgpu_finalize
+
+     INTEGER(C_INT) FUNCTION cdfgpu_synchronize() BIND(C, NAME='cdfgpu_synchronize')
+       IMPORT :: C_INT
+     END FUNCTION cdfgpu_synchronize
+
+     TYPE(C_PTR) FUNCTION cdfgpu_last_error() BIND(C, NAME='cdfgpu_last_error')
+       IMPORT :: C_PTR
+     END FUNCTION cdfgpu_last_error
+
+     TYPE(C_PTR) FUNCTION cdfgpu_pinned_alloc(nbytes) BIND(C, NAME='cdfgpu_pinned_alloc')
+       IMPORT :: C_PTR, C_SIZE_T
+       INTEGER(C_SIZE_T), VALUE :: nbytes
+     END FUNCTION cdfgpu_pinned_alloc
+
+     INTEGER(C_INT) FUNCTION cdfgpu_pinned_free(p) BIND(C, NAME='cdfgpu_pinned_free')
+       IMPORT :: C_INT, C_PTR
+       TYPE(C_PTR), VALUE :: p
+     END FUNCTION cdfgpu_pinned_free
+
+     ! ---- cdfmoc ------------------------------------------------------------
+     INTEGER(C_INT) FUNCTION cdfmoc_gpu_setup(nx, ny, nz, nb, e1v, e3v, ibmask) BIND(C, NAME='cdfmoc_gpu_setup')
+       IMPORT :: C_INT, C_FLOAT, C_INT16_T
+       INTEGER(C_INT), VALUE :: nx, ny, nz, nb
+       REAL(C_FLOAT),      INTENT(in) :: e1v(*), e3v(*)      ! e3v already * vmask (cdfmoc.f90:590-594)
+       INTEGER(C_INT16_T), INTENT(in) :: ibmask(*)           ! (nbasins,npiglo,npjglo), cdfmoc.f90:325-336
+     END FUNCTION cdfmoc_gpu_setup
+
+     INTEGER(C_INT) FUNCTION cdfmoc_gpu_set_e3v(e3v) BIND(C, NAME='cdfmoc_gpu_set_e3v')
+       IMPORT :: C_INT, C_FLOAT
+       REAL(C_FLOAT), INTENT(in) :: e3v(*)                   ! -vvl: per-record e3v * vmask
+     END FUNCTION cdfmoc_gpu_set_e3v
+
+     INTEGER(C_INT) FUNCTION cdfmoc_gpu_submit(slot, jt, zv) BIND(C, NAME='cdfmoc_gpu_submit')
+       IMPORT :: C_INT, C_FLOAT
+       INTEGER(C_INT), VALUE :: slot, jt
+       REAL(C_FLOAT), INTENT(in) :: zv(*)                    ! (npiglo,npjglo,npk-1), pinned
+     END FUNCTION cdfmoc_gpu_submit
+
+     INTEGER(C_INT) FUNCTION cdfmoc_gpu_fetch(slot, dmoc) BIND(C, NAME='cdfmoc_gpu_fetch')
+       IMPORT :: C_INT, C_DOUBLE
+       INTEGER(C_INT), VALUE :: slot
+       REAL(C_DOUBLE), INTENT(out) :: dmoc(*)                ! (nbasins,npjglo,npk), Sv, integrated
+     END FUNCTION cdfmoc_gpu_fetch
+
+     INTEGER(C_INT) FUNCTION cdfmoc_gpu_teardown() BIND(C, NAME='cdfmoc_gpu_teardown')
+       IMPORT :: C_INT
+     END FUNCTION cdfmoc_gpu_teardown
+
+     ! ---- cdfmocsig ---------------------------------------------------------
+     INTEGER(C_INT) FUNCTION cdfmocsig_gpu_setup(nx, ny, nz, nb, nbins, sigmin, sigstp, pref, eos, e1v, e3v, &
+          &                                      ibmask, zspv, zspt, zsps, j_first_global, ny_global)         &
+          &                                      BIND(C, NAME='cdfmocsig_gpu_setup')
+       IMPORT :: C_INT, C_FLOAT, C_INT16_T, C_PTR
+       INTEGER(C_INT), VALUE :: nx, ny, nz, nb, nbins, eos, j_first_global, ny_global
+       REAL(C_FLOAT),  VALUE :: sigmin, sigstp, pref, zspv, zspt, zsps
+       REAL(C_FLOAT),      INTENT(in) :: e1v(*)
+       TYPE(C_PTR), VALUE             :: e3v                 ! C_LOC(e3v3d) (UNmasked), or C_NULL_PTR with -vvl
+       INTEGER(C_INT16_T), INTENT(in) :: ibmask(*)
+     END FUNCTION cdfmocsig_gpu_setup
+
+     INTEGER(C_INT) FUNCTION cdfmocsig_gpu_submit(slot, jt, zv, zt, zs, zveiv, e3v_vvl) BIND(C, NAME='cdfmocsig_gpu_submit')
+       IMPORT :: C_INT, C_FLOAT, C_PTR
+       INTEGER(C_INT), VALUE :: slot, jt
+       REAL(C_FLOAT), INTENT(in) :: zv(*), zt(*), zs(*)      ! raw file values, (npiglo,npjglo,npk-1), pinned
+       TYPE(C_PTR), VALUE :: zveiv, e3v_vvl                  ! C_LOC(...) or C_NULL_PTR
+     END FUNCTION cdfmocsig_gpu_submit
+
+     INTEGER(C_INT) FUNCTION cdfmocsig_gpu_fetch(slot, dmoc) BIND(C, NAME='cdfmocsig_gpu_fetch')
+       IMPORT :: C_INT, C_DOUBLE
+       INTEGER(C_INT), VALUE :: slot
+       REAL(C_DOUBLE), INTENT(out) :: dmoc(*)                ! (nbasins,nbins,npjglo), Sv, integrated
+     END FUNCTION cdfmocsig_gpu_fetch
+
+     INTEGER(C_INT) FUNCTION cdfmocsig_gpu_teardown() BIND(C, NAME='cdfmocsig_gpu_teardown')
+       IMPORT :: C_INT
+     END FUNCTION cdfmocsig_gpu_teardown
+  END INTERFACE
+
+CONTAINS
+
+  SUBROUTINE cdfgpu_check(kerr, cdwhere)
+    !!---------------------------------------------------------------------
+    !! Every non-zero status of the library is fatal for the tool: print the
+    !! library's message and STOP 97 (the reference uses STOP 99 for usage /
+    !! missing files and STOP 98 for NetCDF errors; 97 is new and GPU-specific).
+    !!---------------------------------------------------------------------
+    INTEGER(C_INT),   INTENT(in) :: kerr
+    CHARACTER(LEN=*), INTENT(in) :: cdwhere
+    CHARACTER(KIND=C_CHAR), POINTER :: cl_msg(:)
+    INTEGER :: ji
+    IF ( kerr == CDFGPU_OK ) RETURN
+    CALL C_F_POINTER(cdfgpu_last_error(), cl_msg, (/512/))
+    PRINT *, ' ERROR in ', TRIM(cdwhere), ' : libcdfgpu status ', kerr
+    DO ji = 1, 512
+       IF ( cl_msg(ji) == C_NULL_CHAR ) EXIT
+       WRITE(*,'(a)', ADVANCE='NO') cl_msg(ji)
+    END DO
+    PRINT *
+    STOP 97
+  END SUBROUTINE cdfgpu_check
+
+  FUNCTION cdfgpu_pinned_r4_3d(kpi, kpj, kpk) RESULT(ptab)
+    !!---------------------------------------------------------------------
+    !! Page-locked REAL(4) (kpi,kpj,kpk) buffer for NF90_GET_VAR to fill: the
+    !! H2D copy of a record then runs asynchronously on the library's copy
+    !! stream and overlaps the previous record's kernel.
+    !!---------------------------------------------------------------------
+    INTEGER(KIND=4), INTENT(in) :: kpi, kpj, kpk
+    REAL(KIND=4), POINTER :: ptab(:,:,:)
+    TYPE(C_PTR) :: cl_p
+    cl_p = cdfgpu_pinned_alloc( INT(kpi,C_SIZE_T)*INT(kpj,C_SIZE_T)*INT(kpk,C_SIZE_T)*4_C_SIZE_T )
+    IF ( .NOT. C_ASSOCIATED(cl_p) ) THEN
+       PRINT *, ' ERROR : cdfgpu_pinned_alloc failed' ; STOP 97
+    ENDIF
+    CALL C_F_POINTER(cl_p, ptab, (/kpi, kpj, kpk/))
+  END FUNCTION cdfgpu_pinned_r4_3d
+
+END MODULE cdfgpu
