@@ -61,6 +61,33 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return SO
 
 
+HOST = CSRC / "host"
+HOST_TOOLS = {"cdfmoc_gpu": "cdfmoc_main.cpp", "cdfmocsig_gpu": "cdfmocsig_main.cpp", "nc3dump": "nc3dump_main.cpp"}
+
+
+def build_host(force: bool = False) -> dict:
+    """C++ twins of the cdfmoc / cdfmocsig command lines (NetCDF-3 I/O + the C ABI) into cdftools_b200/bin/."""
+    build(force=False)
+    bindir = PKG / "bin"
+    bindir.mkdir(exist_ok=True)
+    out = {}
+    cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
+    hdrs = [HOST / "nc3.hpp", HOST / "host_common.hpp", PKG.parent / "include" / "cdfgpu.h"]
+    for name, src in HOST_TOOLS.items():
+        exe = bindir / name
+        deps = [HOST / src] + hdrs + ([SO] if name != "nc3dump" else [])
+        if force or not exe.exists() or any(d.stat().st_mtime > exe.stat().st_mtime for d in deps):
+            cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-ffp-contract=off", "-o", str(exe), str(HOST / src)]
+            if name != "nc3dump":
+                cmd += ["-L" + str(PKG), "-lcdfgpu", "-Wl,-rpath," + str(PKG), "-Wl,-rpath,$ORIGIN/.."]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("g++ failed for %s:\n%s" % (name, (r.stdout + r.stderr)[-4000:]))
+        out[name] = exe
+    return out
+
+
 if __name__ == "__main__":
     p = build(force="--force" in sys.argv, verbose=True)
     print("built", p)
+    print("built", ", ".join(str(v) for v in build_host(force="--force" in sys.argv).values()))

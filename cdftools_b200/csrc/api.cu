@@ -21,6 +21,7 @@ struct Ctx {
     int sm_count = 0;
     cudaStream_t s_compute = nullptr, s_copy = nullptr, s_d2h = nullptr;
     unsigned long long launches = 0;
+    bool big_endian_input = false;
 };
 static Ctx g;
 
@@ -37,6 +38,15 @@ struct Slot {
     bool used = false;
     int jt = -1;
 };
+
+static int swap_record(float *d, size_t n, cudaStream_t st)
+{
+    if (!g.big_endian_input) return CDFGPU_OK;
+    bswap32_kernel<<<g.sm_count * 8, 256, 0, st>>>(reinterpret_cast<uint32_t *>(d), n);
+    CDF_CUDA(cudaGetLastError());
+    ++g.launches;
+    return CDFGPU_OK;
+}
 
 static int make_ws(Workspace &w, int ny)
 {
@@ -375,6 +385,11 @@ int cdfgpu_pinned_free(void *p)
     return CDFGPU_OK;
 }
 unsigned long long cdfgpu_launch_count(void) { return g.launches; }
+int cdfgpu_set_input_big_endian(int on)
+{
+    g.big_endian_input = on != 0;
+    return CDFGPU_OK;
+}
 
 // --------------------------------------------------------------------------------------------------- cdfmoc
 int cdfmoc_gpu_teardown(void)
@@ -487,8 +502,10 @@ int cdfmoc_gpu_submit(int slot, int jt, const float *zv)
     CDF_CUDA(cudaMemcpyAsync(s.d_in[0], zv, moc.in_elems() * sizeof(float), cudaMemcpyHostToDevice, g.s_copy));
     CDF_CUDA(cudaEventRecord(s.ev_h2d, g.s_copy));
     CDF_CUDA(cudaStreamWaitEvent(g.s_compute, s.ev_h2d, 0));
+    int rc = swap_record(s.d_in[0], moc.in_elems(), g.s_compute);
+    if (rc) return rc;
     CDF_CUDA(cudaEventRecord(s.ev_k0, g.s_compute));
-    int rc = moc_launch(s.d_in[0], s.d_out, moc.ws_int, g.s_compute);
+    rc = moc_launch(s.d_in[0], s.d_out, moc.ws_int, g.s_compute);
     if (rc) return rc;
     CDF_CUDA(cudaEventRecord(s.ev_k1, g.s_compute));
     s.used = true;

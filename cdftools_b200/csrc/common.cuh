@@ -59,4 +59,21 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// K3: in-place 32-bit byte swap of a record (big-endian NetCDF-3 REAL(4) -> host order).  HBM-bound, 8 B per value.
+__global__ void bswap32_kernel(uint32_t *__restrict__ p, size_t n)
+{
+    const size_t n4 = n >> 2;
+    uint4 *p4 = reinterpret_cast<uint4 *>(p);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 v = p4[i];
+        v.x = __byte_perm(v.x, 0, 0x0123); v.y = __byte_perm(v.y, 0, 0x0123);
+        v.z = __byte_perm(v.z, 0, 0x0123); v.w = __byte_perm(v.w, 0, 0x0123);
+        p4[i] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const size_t i = (n4 << 2) + threadIdx.x;
+        p[i] = __byte_perm(p[i], 0, 0x0123);
+    }
+}
+
 }  // namespace cdfgpu

@@ -1,0 +1,218 @@
+// host_common.hpp -- shared host logic of the C++ twins of cdfmoc / cdfmocsig (names, files, masks, output file).
+// Mirrors, for the hot path only: src/modcdfnames.F90:17-187,362-388 (default names, CDFT_* environment),
+// src/cdfio.F90 (chkfile :3032-3070, SetMeshZgrVersion :3310-3335, getvar name mapping :1510-1536, getvare3 :2221-2274),
+// src/cdfmoc.f90:325-336 / src/cdfmocsig.f90:347-359 (basin mask assembly), cdfmoc.f90:1019-1028,1182-1186 (output).
+#pragma once
+#include <math.h>
+#include <stdlib.h>
+#include <sys/stat.h>
+
+#include <string>
+#include <vector>
+
+#include "../../../include/cdfgpu.h"
+#include "nc3.hpp"
+
+namespace cdfhost {
+
+struct Names {  // modcdfnames.F90 defaults
+    std::string x = "x", y = "y", z = "depth", t = "time_counter";
+    std::string vomecrty = "vomecrty", vomeeivv = "vomeeivv", votemper = "votemper", vosaline = "vosaline";
+    std::string e1v = "e1v", gphiv = "gphiv", vmask = "vmask", tmaskatl = "tmaskatl", tmaskind = "tmaskind",
+                tmaskpac = "tmaskpac", vtimec = "time_counter", vdepthw = "depthw", vlon2d = "nav_lon", vlat2d = "nav_lat";
+    std::string fhgr = "mesh_hgr.nc", fzgr = "mesh_zgr.nc", fmsk = "mask.nc", fbasins = "new_maskglo.nc";
+    std::string missing = "_FillValue";
+    Names()
+    {  // chkenv, modcdfnames.F90:376-380
+        auto env = [](const char *n, std::string &dst) { const char *e = getenv(n); if (e && *e) dst = e; };
+        env("CDFT_MESH_HGR", fhgr); env("CDFT_MESH_ZGR", fzgr); env("CDFT_MASK", fmsk); env("CDFT_BASINS", fbasins);
+    }
+};
+
+// chkfile (cdfio.F90:3032-3070): returns true when the file is MISSING (and says so), like the reference
+inline bool chkfile(const std::string &f, bool verbose = true)
+{
+    if (f == "none") return false;
+    struct stat st;
+    if (stat(f.c_str(), &st) == 0) return false;
+    if (verbose) printf(" %s is missing \n", f.c_str());
+    return true;
+}
+
+[[noreturn]] inline void stop(int code) { fflush(stdout); exit(code); }
+inline void gpu_check(int rc, const char *where)
+{
+    if (rc == CDFGPU_OK) return;
+    printf(" ERROR in %s : libcdfgpu status %d : %s\n", where, rc, cdfgpu_last_error());
+    stop(97);
+}
+inline void nc_check(bool ok, const std::string &err)
+{
+    if (ok) return;
+    printf(" ERROR : %s\n", err.c_str());
+    stop(98);  // the reference STOPs 98 on NetCDF errors (cdfio.F90:2937)
+}
+
+struct MeshZgr {
+    nc3::Reader nc;
+    std::string ver;  // v3.0 | v3.6 (v2.0 partial-step files are not supported by this twin)
+    void open(const std::string &path)
+    {
+        nc_check(nc.open(path), nc.err);
+        const int iv = nc.find_var("e3t_0");
+        if (iv < 0) { printf(" ERROR : %s is a v2.0 mesh_zgr file (e3v_ps): not supported by the GPU twin\n", path.c_str()); stop(98); }
+        int nsp = 0;  // number of non-record, non-singleton dims
+        for (int d : nc.vars[iv].dimids) if (nc.dims[d].len > 1 && d != nc.recdim) ++nsp;
+        ver = (nsp <= 1) ? "v3.0" : "v3.6";
+        printf("  mesh_zgr version is %s\n", ver.c_str());
+    }
+    std::string e3v_name() const { return ver == "v3.0" ? "e3v" : "e3v_0"; }
+    std::string name1d(const std::string &base) const  // gdepw / gdept / e3t1d
+    {
+        if (base == "gdepw") return ver == "v3.0" ? "gdepw_0" : "gdepw_1d";
+        if (base == "gdept") return ver == "v3.0" ? "gdept_0" : "gdept_1d";
+        return ver == "v3.0" ? "e3t_0" : "e3t_1d";
+    }
+};
+
+// one (ny,nx) level of a (t,z,y,x) / (z,y,x) / (y,x) variable, like getvar(cdfile, cdvar, klev, kpi, kpj, ktime)
+inline void read_level(nc3::Reader &nc, const std::string &var, int klev /*0-based*/, long rec, size_t nxy, float *out)
+{
+    const int iv = nc.find_var(var);
+    if (iv < 0) { printf(" ERROR : variable %s not found in %s\n", var.c_str(), nc.path.c_str()); stop(98); }
+    const nc3::Var &v = nc.vars[iv];
+    const uint64_t nlev = v.nelem_per_rec / nxy;
+    const uint64_t off = (nlev > 1 ? (uint64_t)klev : 0) * nxy;
+    nc_check(nc.read_f32(v, v.isrec ? rec : 0, off, nxy, out), nc.err);
+}
+inline void read_1d(nc3::Reader &nc, const std::string &var, size_t n, float *out)
+{
+    const int iv = nc.find_var(var);
+    if (iv < 0) { printf(" ERROR : variable %s not found in %s\n", var.c_str(), nc.path.c_str()); stop(98); }
+    nc_check(nc.read_f32(nc.vars[iv], 0, 0, n, out), nc.err);
+}
+
+// ibmask(nb,nx,ny): 1 global(vmask k=1), 2 atl, 3 indo-pacific = min(1,pac+ind), 4 ind, 5 pac  (cdfmoc.f90:325-336)
+inline void basin_masks(const Names &cn, bool lbas, int nx, int ny, bool zero_edges, std::vector<int16_t> &ib)
+{
+    const int nb = lbas ? 5 : 1;
+    const size_t nxy = (size_t)nx * ny;
+    ib.assign(nxy * nb, 0);
+    std::vector<float> tmp(nxy);
+    nc3::Reader msk;
+    nc_check(msk.open(cn.fmsk), msk.err);
+    read_level(msk, cn.vmask, 0, 0, nxy, tmp.data());
+    for (size_t c = 0; c < nxy; ++c) ib[c * nb] = (int16_t)tmp[c];
+    if (lbas) {
+        nc3::Reader bas;
+        nc_check(bas.open(cn.fbasins), bas.err);
+        const std::string *names[3] = {&cn.tmaskatl, &cn.tmaskind, &cn.tmaskpac};
+        const int slot[3] = {1, 3, 4};
+        for (int m = 0; m < 3; ++m) {
+            read_level(bas, *names[m], 0, 0, nxy, tmp.data());
+            for (size_t c = 0; c < nxy; ++c) ib[c * nb + slot[m]] = (int16_t)tmp[c];
+        }
+        for (size_t c = 0; c < nxy; ++c) {
+            int16_t s = (int16_t)(ib[c * nb + 4] + ib[c * nb + 3]);
+            ib[c * nb + 2] = s > 0 ? (int16_t)1 : s;
+        }
+    }
+    if (zero_edges)
+        for (int j = 0; j < ny; ++j) { ib[((size_t)j * nx) * nb] = 0; ib[((size_t)j * nx + nx - 1) * nb] = 0; }
+}
+
+// nav_lat(1,:) = gphiv(iloc(1),:) with iloc = MAXLOC(gphiv) (cdfmoc.f90:316-318): first maximum in column-major order
+inline void dummy_lat(const std::vector<float> &gphiv, int nx, int ny, std::vector<float> &lat)
+{
+    size_t imax = 0;
+    float best = gphiv[0];
+    for (size_t c = 1; c < (size_t)nx * ny; ++c)
+        if (gphiv[c] > best) { best = gphiv[c]; imax = c; }
+    const int i = (int)(imax % nx);
+    lat.resize(ny);
+    for (int j = 0; j < ny; ++j) lat[j] = gphiv[(size_t)j * nx + i];
+}
+
+struct OutVar { std::string name, long_name, units; float valid_min, valid_max; };
+
+// create + createvar + putheadervar + putvar1d for the (t, depth|sigma, y, x=1) output files
+// (cdfio.F90:260-368,371-459,629-682,2290-2407; cdfmoc.f90:1019-1028,1182-1186; cdfmocsig.f90:502-510,576-581)
+struct OutFile {
+    nc3::Writer w;
+    std::vector<int> varids;
+    int ny = 0, nlev = 0;
+    void create(const std::string &path, const std::string &zdim, int ny_, int nlev_, const std::vector<OutVar> &vars,
+                const std::string &history, const std::vector<float> &navlat, const std::vector<float> &zaxis,
+                const std::vector<double> &tim, nc3::Reader &ref)
+    {
+        ny = ny_; nlev = nlev_;
+        const int dx = w.def_dim("x", 1), dy = w.def_dim("y", ny), dz = w.def_dim(zdim, nlev), dt = w.def_dim("time_counter", 0);
+        const int vlon = w.def_var("nav_lon", nc3::NC_FLOAT, {dy, dx});
+        const int vlat = w.def_var("nav_lat", nc3::NC_FLOAT, {dy, dx});
+        const int vz = w.def_var(zdim, nc3::NC_FLOAT, {dz});
+        const int vt = w.def_var("time_counter", nc3::NC_DOUBLE, {dt});
+        // copyatt of the time variable from the reference file (cdfio.F90:353-354)
+        const int it = ref.find_var("time_counter");
+        if (it >= 0)
+            for (auto &a : ref.vars[it].atts)
+                if (a.type == nc3::NC_CHAR) w.put_att_text(vt, a.name, a.as_string());
+        // global attributes (cdfio.F90:360-363) taken from the reference file when present (getdim caches them, :939-994)
+        auto gatt = [&](const char *n, const char *dflt) {
+            for (auto &a : ref.gatts) if (a.name == n && a.type == nc3::NC_CHAR) return a.as_string();
+            return std::string(dflt);
+        };
+        int start_date = -1;
+        for (auto &a : ref.gatts) if (a.name == "start_date") start_date = (int)a.as_double();
+        w.put_att_int(-1, "start_date", start_date);
+        w.put_att_text(-1, "output_frequency", gatt("output_frequency", "N/A"));
+        w.put_att_text(-1, "CONFIG", gatt("CONFIG", "N/A"));
+        w.put_att_text(-1, "CASE", gatt("CASE", "N/A"));
+        for (auto &v : vars) {
+            const int id = w.def_var(v.name, nc3::NC_FLOAT, {dt, dz, dy, dx});
+            w.put_att_text(id, "units", v.units);
+            w.put_att_float(id, "_FillValue", 99999.f);
+            w.put_att_float(id, "valid_min", v.valid_min);
+            w.put_att_float(id, "valid_max", v.valid_max);
+            w.put_att_text(id, "long_name", v.long_name);
+            w.put_att_text(id, "short_name", v.name);
+            w.put_att_int(id, "iweight", 1);
+            w.put_att_text(id, "online_operation", "N/A");
+            w.put_att_text(id, "axis", "TZY");
+            w.put_att_float(id, "scale_factor", 1.f);
+            w.put_att_float(id, "add_offset", 0.f);
+            w.put_att_float(id, "savelog10", 0.f);
+            varids.push_back(id);
+        }
+        w.put_att_text(-1, "history", history);
+        nc_check(w.create(path), w.err);
+        std::vector<float> zero(ny, 0.f);
+        w.put_f32(vlon, 0, 0, ny, zero.data());
+        w.put_f32(vlat, 0, 0, ny, navlat.data());
+        w.put_f32(vz, 0, 0, nlev, zaxis.data());
+        for (size_t r = 0; r < tim.size(); ++r) w.put_f64(vt, (long)r, 0, 1, &tim[r]);
+    }
+    // one record of one variable: vals[lev][j]
+    void put(int v, long rec, const float *vals) { nc_check(w.put_f32(varids[v], rec, 0, (uint64_t)nlev * ny, vals), w.err); }
+};
+
+// pinned record buffers
+struct Pinned {
+    float *p = nullptr;
+    explicit Pinned(size_t n) { p = (float *)cdfgpu_pinned_alloc(n * sizeof(float)); if (!p) { printf(" ERROR : %s\n", cdfgpu_last_error()); stop(97); } }
+    ~Pinned() { cdfgpu_pinned_free(p); }
+    Pinned(const Pinned &) = delete;
+};
+
+// a whole (nz-1, ny, nx) record of `var`: raw big-endian bytes when the variable is plain float32 (the GPU swaps),
+// converted on the host otherwise.  Returns true when the raw path was used.
+inline bool read_record(nc3::Reader &nc, const std::string &var, long rec, size_t n, float *dst, bool allow_raw)
+{
+    const int iv = nc.find_var(var);
+    if (iv < 0) { printf(" ERROR : variable %s not found in %s\n", var.c_str(), nc.path.c_str()); stop(98); }
+    const nc3::Var &v = nc.vars[iv];
+    if (allow_raw && nc.is_plain_f32(v)) { nc_check(nc.read_raw(v, rec, 0, n, dst), nc.err); return true; }
+    nc_check(nc.read_f32(v, rec, 0, n, dst), nc.err);
+    return false;
+}
+
+}  // namespace cdfhost

@@ -29,6 +29,7 @@ SIGNATURES = {
     "cdfgpu_pinned_alloc": (C.c_void_p, [C.c_size_t]),
     "cdfgpu_pinned_free": (C.c_int, [C.c_void_p]),
     "cdfgpu_launch_count": (C.c_ulonglong, []),
+    "cdfgpu_set_input_big_endian": (C.c_int, [C.c_int]),
     "cdfmoc_gpu_setup": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cdfmoc_gpu_set_e3v": (C.c_int, [C.c_void_p]),
     "cdfmoc_gpu_submit": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
@@ -121,6 +122,10 @@ def device_count() -> int:
 
 def launch_count() -> int:
     return int(load().cdfgpu_launch_count())
+
+
+def set_input_big_endian(on: bool):
+    _chk(load().cdfgpu_set_input_big_endian(int(bool(on))), "cdfgpu_set_input_big_endian")
 
 
 class PinnedArray:

@@ -1,0 +1,91 @@
+"""Writes a synthetic configuration as the NetCDF-3 (64-bit offset) files cdfmoc / cdfmocsig read
+(SURVEY.md App. B): mesh_hgr.nc, mesh_zgr.nc (v3.6 naming, cdfio.F90:3323-3331), mask.nc, new_maskglo.nc and the
+gridV / gridT record files.  Uses scipy.io.netcdf_file (the only NetCDF writer in this image); reading them back in
+the product is done by the self-contained C++ reader (csrc/host/nc3.hpp)."""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+from scipy.io import netcdf_file
+
+from . import synth
+
+
+def _new(path, dims, version=2):
+    f = netcdf_file(str(path), "w", version=version)
+    for n, l in sorted(dims.items(), key=lambda kv: kv[1] is not None):   # scipy wants the unlimited dimension first
+        f.createDimension(n, l)
+    return f
+
+
+def write_mesh(m: synth.Mesh, outdir, with_basins=True, version=2):
+    out = Path(outdir)
+    out.mkdir(parents=True, exist_ok=True)
+    nz, ny, nx = m.e3v_0.shape
+    f = _new(out / "mesh_hgr.nc", {"x": nx, "y": ny, "t": None}, version)
+    for name, arr in (("e1v", m.e1v), ("e1u", m.e1u), ("gphiv", m.gphiv), ("glamv", m.glamv)):
+        v = f.createVariable(name, "f", ("t", "y", "x"))
+        v[0] = arr
+    f.close()
+    f = _new(out / "mesh_zgr.nc", {"x": nx, "y": ny, "z": nz, "t": None}, version)
+    v = f.createVariable("e3v_0", "f", ("t", "z", "y", "x")); v[0] = m.e3v_0
+    v = f.createVariable("e3t_0", "f", ("t", "z", "y", "x")); v[0] = m.e3v_0     # presence + rank select 'v3.6'
+    for name, arr in (("gdepw_1d", m.gdepw_1d), ("gdept_1d", m.gdept_1d), ("e3t_1d", m.e3t_1d)):
+        v = f.createVariable(name, "f", ("t", "z")); v[0] = arr
+    f.close()
+    f = _new(out / "mask.nc", {"x": nx, "y": ny, "z": nz, "t": None}, version)
+    for name, arr in (("vmask", m.vmask), ("tmask", m.tmask), ("umask", m.umask)):
+        v = f.createVariable(name, "b", ("t", "z", "y", "x")); v[0] = arr
+    f.close()
+    if with_basins:
+        f = _new(out / "new_maskglo.nc", {"x": nx, "y": ny}, version)
+        for name, arr in (("tmaskatl", m.tmaskatl), ("tmaskind", m.tmaskind), ("tmaskpac", m.tmaskpac)):
+            v = f.createVariable(name, "f", ("y", "x")); v[:] = arr
+        f.close()
+
+
+def write_gridv(m: synth.Mesh, path, nrec, spval=0.0, adversarial=False, eiv=False, version=2):
+    nz, ny, nx = m.e3v_0.shape
+    f = _new(path, {"x": nx, "y": ny, "depthv": nz, "time_counter": None}, version)
+    f.start_date = np.int32(20260101)
+    f.output_frequency = "5d"
+    f.CONFIG = m.meta.get("grid", "SYN")
+    f.CASE = "B200"
+    tc = f.createVariable("time_counter", "d", ("time_counter",))
+    tc.units = "seconds since 2026-01-01 00:00:00"
+    v = f.createVariable("vomecrty", "f", ("time_counter", "depthv", "y", "x"))
+    v.missing_value = np.float32(spval)
+    e = None
+    if eiv:
+        e = f.createVariable("vomeeivv", "f", ("time_counter", "depthv", "y", "x"))
+        e.missing_value = np.float32(spval)
+    recs = []
+    for r in range(nrec):
+        tc[r] = 432000.0 * (r + 0.5)
+        rec = synth.make_v_record(m, r, adversarial=adversarial, spval=spval if spval else None)
+        v[r] = rec
+        recs.append(rec)
+        if e is not None:
+            e[r] = (0.01 * synth.make_v_record(m, 1000 + r)).astype(np.float32)
+    f.close()
+    return recs
+
+
+def write_gridt(m: synth.Mesh, path, nrec, spval=0.0, version=2):
+    nz, ny, nx = m.e3v_0.shape
+    f = _new(path, {"x": nx, "y": ny, "deptht": nz, "time_counter": None}, version)
+    tc = f.createVariable("time_counter", "d", ("time_counter",))
+    t = f.createVariable("votemper", "f", ("time_counter", "deptht", "y", "x"))
+    s = f.createVariable("vosaline", "f", ("time_counter", "deptht", "y", "x"))
+    t.missing_value = np.float32(spval)
+    s.missing_value = np.float32(spval)
+    recs = []
+    for r in range(nrec):
+        tc[r] = 432000.0 * (r + 0.5)
+        tt, ss = synth.make_ts_record(m, r, spval=spval if spval else None)
+        t[r] = tt
+        s[r] = ss
+        recs.append((tt, ss))
+    f.close()
+    return recs

@@ -65,6 +65,10 @@ void *cdfgpu_pinned_alloc(size_t nbytes);
 int cdfgpu_pinned_free(void *p);
 /* Number of kernels this library has launched since cdfgpu_init (bench.py's gpu_launches). */
 unsigned long long cdfgpu_launch_count(void);
+/* K3: records handed to *_submit are RAW big-endian NetCDF-3 bytes (what fread delivers; the XDR decode libnetcdf
+ * does on the CPU inside NF90_GET_VAR, src/cdfio.F90:1593): the byte swap then runs on the device, fused in front of
+ * the record's kernel.  on = 0 (default): host-endian REAL(4) as NF90_GET_VAR returns them. */
+int cdfgpu_set_input_big_endian(int on);
 
 /* ---- cdfmoc: depth-space MOC ------------------------------------------------------------------------------
  * setup   replaces the one-time part of src/cdfmoc.f90:306,325-336,343-348:

@@ -1,0 +1,60 @@
+"""Host side above the C ABI: the self-contained NetCDF-3 reader/writer and the command-line contracts of the C++
+twins (exit codes of the reference: STOP 99 usage/missing file/unknown option).  CPU only."""
+import json
+import subprocess
+
+import numpy as np
+import pytest
+from scipy.io import netcdf_file
+
+from cdftools_b200 import build, ncfiles, synth
+
+
+@pytest.fixture(scope="module")
+def tools():
+    return build.build_host()
+
+
+@pytest.mark.parametrize("version", [1, 2])
+def test_reader_parses_scipy_files(tools, tmp_path, version):
+    m = synth.make_mesh("TINY")
+    ncfiles.write_mesh(m, tmp_path, version=version)
+    recs = ncfiles.write_gridv(m, tmp_path / "gridV.nc", 3, spval=1.0e20, version=version)
+    d = json.loads(subprocess.run([tools["nc3dump"], tmp_path / "gridV.nc"], capture_output=True, text=True, check=True).stdout)
+    assert d["version"] == version and d["numrecs"] == 3
+    assert d["dims"] == {"x": m.nx, "y": m.ny, "depthv": m.nz, "time_counter": 3}
+    v = d["vars"]["vomecrty"]
+    allv = np.stack(recs).astype(np.float64)
+    assert v["nelem"] == allv.size and v["spval"] == pytest.approx(1.0e20)
+    assert v["abssum"] == pytest.approx(np.abs(allv).sum(), rel=1e-12)
+    assert d["vars"]["time_counter"]["sum"] == pytest.approx(sum(432000.0 * (r + 0.5) for r in range(3)))
+    d = json.loads(subprocess.run([tools["nc3dump"], tmp_path / "mask.nc"], capture_output=True, text=True, check=True).stdout)
+    assert d["vars"]["vmask"]["sum"] == float(m.vmask.sum())       # NC_BYTE variables
+    d = json.loads(subprocess.run([tools["nc3dump"], tmp_path / "mesh_zgr.nc"], capture_output=True, text=True, check=True).stdout)
+    assert d["vars"]["e3v_0"]["sum"] == pytest.approx(float(m.e3v_0.astype(np.float64).sum()), rel=1e-12)
+
+
+def test_reader_rejects_non_netcdf(tools, tmp_path):
+    p = tmp_path / "x.nc"
+    p.write_bytes(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
+    r = subprocess.run([tools["nc3dump"], p], capture_output=True, text=True)
+    assert r.returncode == 98 and "not a NetCDF classic file" in r.stdout
+
+
+@pytest.mark.parametrize("tool", ["cdfmoc_gpu", "cdfmocsig_gpu"])
+def test_cli_contracts(tools, tmp_path, tool):
+    # no argument: usage, normal termination (cdfmoc.f90:129-209)
+    r = subprocess.run([tools[tool]], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0 and "usage" in r.stdout
+    # unknown option: STOP 99 (cdfmoc.f90:232, cdfmocsig.f90:206)
+    r = subprocess.run([tools[tool], "-v", "V.nc", "-bogus"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 99 and "unknown option" in r.stdout
+    # missing files: STOP 99 (cdfmoc.f90:246, cdfmocsig.f90:224)
+    args = ["-v", "V.nc"] if tool == "cdfmoc_gpu" else ["-v", "V.nc", "-t", "T.nc", "-r", "0"]
+    r = subprocess.run([tools[tool]] + args, capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 99 and "is missing" in r.stdout
+
+
+def test_cdfmocsig_needs_three_mandatory_arguments(tools, tmp_path):
+    r = subprocess.run([tools["cdfmocsig_gpu"], "-v", "V.nc", "-t", "T.nc"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 99 and "mandatory arguments missing" in r.stdout
