@@ -50,9 +50,9 @@ static int swap_record(float *d, size_t n, cudaStream_t st)
 
 static int make_ws(Workspace &w, int ny)
 {
-    CDF_CUDA(cudaMalloc(&w.d_tickets, 2 * sizeof(int)));
+    CDF_CUDA(cudaMalloc(&w.d_tickets, 2 * kTicketShards * kTicketStride * sizeof(int)));
     CDF_CUDA(cudaMalloc(&w.d_col, (size_t)ny * sizeof(int)));
-    CDF_CUDA(cudaMemsetAsync(w.d_tickets, 0, 2 * sizeof(int), g.s_compute));
+    CDF_CUDA(cudaMemsetAsync(w.d_tickets, 0, 2 * kTicketShards * kTicketStride * sizeof(int), g.s_compute));
     CDF_CUDA(cudaMemsetAsync(w.d_col, 0, (size_t)ny * sizeof(int), g.s_compute));
     w.parity = 0;
     return CDFGPU_OK;
@@ -204,8 +204,9 @@ static int moc_launch_t(const MocParams &p, cudaStream_t st)
     switch (moc.variant) {
     case 1: return moc_launch_v<NB, 4, 4>(p, st);
     case 2: return moc_launch_v<NB, 2, 4>(p, st);
-    case 3: return moc_launch_v<NB, 8, 2>(p, st);
-    case 4: return moc_launch_v<NB, 6, 2>(p, st);
+    case 3: return moc_launch_v<NB, 3, 3>(p, st);
+    case 4: return moc_launch_v<NB, 5, 2>(p, st);
+    case 5: return moc_launch_v<NB, 3, 4>(p, st);
     }
     return moc_launch_v<NB, 4, 3>(p, st);
 }
@@ -419,8 +420,9 @@ int cdfmoc_gpu_setup(int nx, int ny, int nz, int nb, const float *e1v, const flo
         const char *v = getenv("CDFGPU_K1_VARIANT");
         moc.variant = v ? atoi(v) : 0;
     }
-    // rows shorter than ~16 KB are handed out two levels at a time to halve the ticket traffic
-    moc.chunk = (nx < 4096) ? 2 : 1;
+    // rows shorter than ~16 KB are handed out several levels at a time: fewer tickets, fences and column counters
+    moc.chunk = (nx < 4096) ? 2 : 1;   // levels per work unit (sharded tickets make small units affordable)
+    if (const char *c = getenv("CDFGPU_K1_CHUNK")) moc.chunk = std::max(1, atoi(c));
     const size_t nxy = (size_t)nx * ny;
     CDF_CUDA(cudaMalloc(&moc.d_e1v, nxy * sizeof(float)));
     CDF_CUDA(cudaMalloc(&moc.d_e3m, nxy * (size_t)(nz - 1) * sizeof(float)));

@@ -29,7 +29,7 @@ struct MocParams {
     const uint32_t *__restrict__ maskw; // [4][ny][pitchw] packed basin bits, copy s shifted by s cells
     const int16_t *__restrict__ ibmask; // (ny, nx, nb) for the general path
     double *__restrict__ out;           // (nz, ny, nb)
-    int *tickets;                       // [2] row tickets (ping-pong between launches)
+    int *tickets;                       // [2][kTicketShards*kTicketStride] unit tickets (ping-pong between launches)
     int *col_done;                      // [ny] rows finished per column j (self-resetting)
     int nx, ny, nz, pitchw;
     int parity;                         // launch parity selecting tickets[parity]
@@ -38,6 +38,8 @@ struct MocParams {
 };
 
 constexpr int kMocThreads = 256;
+constexpr int kTicketShards = 32;   // sharded work counters (see moc_zonal_scan_kernel)
+constexpr int kTicketStride = 32;   // ints between shards: one 128-byte line each
 
 // acc -= dp when bit `BIT` of mbits is set.  Written as ONE fused multiply-add with a multiplier of -1.0 or -0.0
 // built from the mask bit (only the high word differs): fma(dp,-1,acc) == acc - dp and fma(dp,-0,acc) == acc, both
@@ -140,17 +142,42 @@ __global__ void __launch_bounds__(kMocThreads, MINB) moc_zonal_scan_kernel(const
     const int warp = threadIdx.x >> 5;
     const int nzm1 = p.nz - 1;
     const uint64_t pol = make_evict_first_policy();
+    // Work units = `chunk` consecutive levels of one latitude row j, numbered j-major.  They are handed out
+    // dynamically, but NOT by one counter: a same-address L2 atomic completes only every ~3.6 ns on B200, so one
+    // ticket per row would cost 0.27 ms per ORCA025 record by itself (measured: chunk=1 0.274 ms vs 0.160 ms).  The
+    // ticket is therefore sharded over kTicketShards counters in different 128-byte lines; shard c owns the units
+    // u = t*kTicketShards + c.  A warp starts on shard (global warp id mod shards) and moves on to the next shard when
+    // its own runs dry (work stealing), so all shards drain together and the tail is at most one unit per warp.
     const int chunks_per_col = (nzm1 + p.chunk - 1) / p.chunk;
     const int nunits = p.ny * chunks_per_col;
-    int *ticket = p.tickets + p.parity;
-    if (blockIdx.x == 0 && threadIdx.x == 0) p.tickets[p.parity ^ 1] = 0;  // re-arm the next launch's counter
-
+    int *tickets = p.tickets + p.parity * (kTicketShards * kTicketStride);
+    {   // re-arm the next launch's counters
+        int *other = p.tickets + (p.parity ^ 1) * (kTicketShards * kTicketStride);
+        if (blockIdx.x == 0 && threadIdx.x < kTicketShards) other[threadIdx.x * kTicketStride] = 0;
+    }
+    int shard = (blockIdx.x * (kMocThreads / 32) + warp) % kTicketShards;
+    auto take = [&](int sh) {   // lane 0: unit index from shard sh (may be >= nunits when the shard is dry)
+        return atomicAdd(tickets + sh * kTicketStride, 1) * kTicketShards + sh;
+    };
     int u = 0;
-    if (lane == 0) u = atomicAdd(ticket, 1);
+    if (lane == 0) u = take(shard);
     u = __shfl_sync(kFull, u, 0);
-    while (u < nunits) {
+    for (;;) {
+        if (u >= nunits) {
+            // this shard is exhausted: look at all shards at once (lane = shard, one L2 read) and steal from the next
+            // one that still has units; when none has, the warp is done.  Counters only grow, so a stale value can
+            // only cause one wasted ticket.
+            const int seen = __ldcg(tickets + lane * kTicketStride) * kTicketShards + lane;
+            unsigned live = __ballot_sync(kFull, seen < nunits);
+            if (live == 0u) break;
+            live = (live >> shard) | (shard ? (live << (32 - shard)) : 0u);   // rotate so that bit 0 = current shard
+            shard = (shard + __ffs(live) - 1) % kTicketShards;
+            if (lane == 0) u = take(shard);
+            u = __shfl_sync(kFull, u, 0);
+            continue;
+        }
         int unext = 0;
-        if (lane == 0) unext = atomicAdd(ticket, 1);  // prefetch the next ticket; latency hidden by the row below
+        if (lane == 0) unext = take(shard);  // request the next unit now; its latency hides behind the rows below
         const int j = u / chunks_per_col;
         const int k0 = (u - j * chunks_per_col) * p.chunk;
         const int k1 = min(k0 + p.chunk, nzm1);
@@ -174,28 +201,32 @@ __global__ void __launch_bounds__(kMocThreads, MINB) moc_zonal_scan_kernel(const
                 }
             }
         }
-        // publish the rows, then count them; the warp that completes column j integrates it vertically
+        // publish the rows, then count them; the warp that completes column j integrates it vertically.
+        // Release on the counting atomic (orders this warp's row stores, made visible to lane 0 by __syncwarp) and
+        // an acquire fence only in the one warp that finishes the column.
         __syncwarp();
         int done = 0;
         if (lane == 0) {
-            __threadfence();
-            done = atomicAdd(p.col_done + j, k1 - k0) + (k1 - k0);
+            int old;
+            asm volatile("atom.add.release.gpu.global.s32 %0, [%1], %2;"
+                         : "=r"(old) : "l"(p.col_done + j), "r"(k1 - k0) : "memory");
+            done = old + (k1 - k0);
         }
         done = __shfl_sync(kFull, done, 0);
         if (done == nzm1) {
-            __threadfence();
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
             double *sc = s_scan + (size_t)warp * nzm1 * NB;
             for (int t = lane; t < nzm1 * NB; t += kWarp) {
-                const int k = t / NB, b = t - k * NB;
-                sc[t] = __ldcg(p.out + ((size_t)k * p.ny + j) * NB + b) / 1.0e6;  // dmoc(:,jj,jk)/1.d6
+                const int kk = t / NB, b = t - kk * NB;
+                sc[t] = __ldcg(p.out + ((size_t)kk * p.ny + j) * NB + b) / 1.0e6;  // dmoc(:,jj,jk)/1.d6
             }
             __syncwarp();
             if (lane < NB) {
                 double psi = 0.0;
                 p.out[((size_t)nzm1 * p.ny + j) * NB + lane] = 0.0;  // dmoc(:,:,npk) stays 0
-                for (int k = nzm1 - 1; k >= 0; --k) {
-                    psi = psi + sc[k * NB + lane];  // dmoc(:,jj,jk+1) + dmoc(:,jj,jk)/1.d6
-                    p.out[((size_t)k * p.ny + j) * NB + lane] = psi;
+                for (int kk = nzm1 - 1; kk >= 0; --kk) {
+                    psi = psi + sc[kk * NB + lane];  // dmoc(:,jj,jk+1) + dmoc(:,jj,jk)/1.d6
+                    p.out[((size_t)kk * p.ny + j) * NB + lane] = psi;
                 }
             }
             if (lane == 0) p.col_done[j] = 0;  // self-reset for the next launch

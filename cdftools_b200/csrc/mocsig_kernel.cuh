@@ -25,7 +25,7 @@
 
 namespace cdfgpu {
 
-constexpr int kSigWarps = 16;
+constexpr int kSigWarps = 24;
 constexpr int kSigThreads = kSigWarps * 32;
 constexpr int kSigMaxPat = 32;
 constexpr int kSigWinVec = 64;  // one warp step = 64 float4 vectors = 256 cells, 8 consecutive cells per lane
@@ -53,6 +53,7 @@ struct SigParams {
     float spv, spt, sps;
     double dlh, dlref;
     double inv_sigstp, qmargin;  // fast bin filter: 1/sigstp and the safety distance to a bin edge (q units); <0: off
+    double dlref_m1000, nbins_d, half_m_margin;   // dlref - 1000, (double)nbins, 0.5 - qmargin
 };
 
 // ---- equation of state ----------------------------------------------------------------------------------------
@@ -179,23 +180,32 @@ __device__ __forceinline__ double eos_dlr123_fma(double t, double s, double h)
     return FM(FM(r3, h, r2), h, r1) * h;   // (dlr3*h + dlr2)*h + dlr1)*h, to be added to dlr0
 }
 
+// sqrt for the fast path: fp32 reciprocal-sqrt seed + two Newton steps in fp64 (branch-free, ~1 ulp).  The exact
+// path keeps the correctly rounded __dsqrt_rn; the difference is covered by the guard (|dsigma/ds| < 4e3).
+__device__ __forceinline__ double fast_sqrt_pos(double x)
+{
+    double y = (double)rsqrtf((float)x);
+    y = y * FM(-0.5 * x, y * y, 1.5);
+    y = y * FM(-0.5 * x, y * y, 1.5);
+    const double sx = x * y;
+    return FM(FM(-sx, sx, x), 0.5 * y, sx);   // one correction step on sqrt itself
+}
+
 template <int EOS, bool SIGMA0>
 __device__ __forceinline__ int sigma_bin_fast(float tem, float sal, const SigParams &p)
 {
     if (EOS == CDFGPU_EOS_NEUTRAL || p.qmargin < 0.0) return sigma_bin<EOS, SIGMA0>(tem, sal, p);
-    const double t = DM((double)tem, 1.0 / 40.0);
-    const double s = __dsqrt_rn(DM(fabs(DA((double)sal, c_eos.rdeltaS)), c_eos.r1_S0));
+    const double t = (double)tem * (1.0 / 40.0);
+    const double s = fast_sqrt_pos(fabs((double)sal + c_eos.rdeltaS) * c_eos.r1_S0);
     double dlr = eos_dlr0_fma(t, s);
     if (!SIGMA0) dlr += eos_dlr123_fma(t, s, p.dlh);
-    double sig = (dlr + p.dlref) - 1000.0;
-    if (sal == 0.0f || sal == p.sps) sig = 0.0;              // dltm / itmask
-    const double qa = (sig - (double)p.sigmin) * p.inv_sigstp;
-    if (fabs(qa) < 2.0e9) {                                   // false for NaN; INT() of huge values is the exact path's job
-        if (qa < 1.0 - p.qmargin) return 1;                   // INT(q) <= 0 -> MAX(ibin,1)
-        if (qa >= (double)p.nbins + p.qmargin) return p.nbins;   // MIN(ibin,nbins)
-        if (fabs(qa - rint(qa)) > p.qmargin) return min(max(__double2int_rz(qa), 1), p.nbins);
-    }
-    return sigma_bin<EOS, SIGMA0>(tem, sal, p);
+    const double qa = ((dlr + p.dlref_m1000) - (double)p.sigmin) * p.inv_sigstp;
+    // common case: strictly inside the bin range, farther than the margin from a bin edge, salinity not a mask value
+    const int ib = __double2int_rz(qa);
+    const double fr = qa - (double)ib;
+    const bool ok = (qa > 1.0) && (qa < p.nbins_d) && (fabs(fr - 0.5) < p.half_m_margin) && (sal != 0.0f) && (sal != p.sps);
+    if (ok) return ib;
+    return sigma_bin<EOS, SIGMA0>(tem, sal, p);   // clamps, land, NaN/Inf, near-edge cells: the reference chain
 }
 #undef FM
 
@@ -296,8 +306,11 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
         const bool skip_row = (p.ny_global > 1) && (jg == 0 || jg == p.ny_global - 1);  // jj = 2..npjglo-1 only
 
         if (!skip_row) {
-            int k = 0, win = warp;
-            while (win >= wpr) { win -= wpr; ++k; }
+            // window id = win*(nz-1) + k (level fastest): a warp's static share w, w+nwarps, ... then sweeps all
+            // longitude sectors and depths, so land/ocean contrasts do not load some warps of the CTA more than others
+            // (with the sector-fastest order and nwarps a multiple of the sectors per row, a warp kept ONE sector).
+            int win = 0, k = warp;
+            while (k >= nzm1) { k -= nzm1; ++win; }
             for (int w = warp; w < total; w += nwarps) {   // warp-uniform loop: one window of 64 vectors per trip
                 const size_t e0 = ((size_t)k * p.ny + j) * (size_t)p.nx;
                 const int s = (int)(e0 & 3);
@@ -410,8 +423,8 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
                     for (int c = 0; c < 8; ++c)
                         if (__any_sync(kFull, key[c] >= 0)) hist_flush(hist, key[c], val[c], lane);
                 }
-                win += nwarps;
-                while (win >= wpr) { win -= wpr; ++k; }
+                k += nwarps;
+                while (k >= nzm1) { k -= nzm1; ++win; }
             }
         }
         __syncthreads();
