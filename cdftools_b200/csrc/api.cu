@@ -120,6 +120,7 @@ struct MocPlan {
     uint32_t *d_maskw = nullptr;
     int16_t *d_ibmask = nullptr;
     int *d_flag = nullptr;
+    float *d_ext = nullptr;   // cdfmaxmoc epilogue result
     Workspace ws_int, ws_ext;
     Slot slots[CDFGPU_MAX_SLOTS];
     int grid = 0;
@@ -398,7 +399,7 @@ int cdfmoc_gpu_teardown(void)
     if (!moc.ready && !moc.d_area) return CDFGPU_OK;
     if (g.inited) cdfgpu_synchronize();
     cudaFree(moc.d_e1v); cudaFree(moc.d_e3m); cudaFree(moc.d_area); cudaFree(moc.d_maskw);
-    cudaFree(moc.d_ibmask); cudaFree(moc.d_flag); cudaFree(moc.d_classes);
+    cudaFree(moc.d_ibmask); cudaFree(moc.d_flag); cudaFree(moc.d_classes); cudaFree(moc.d_ext);
     free_ws(moc.ws_int); free_ws(moc.ws_ext);
     for (auto &s : moc.slots) free_slot(s);
     moc = MocPlan();
@@ -536,6 +537,34 @@ int cdfmoc_gpu_compute_device(const float *d_zv, double *d_dmoc, void *stream)
     REQUIRE(d_zv && d_dmoc, CDFGPU_ERR_ARG, "cdfmoc_gpu_compute_device: null pointer");
     if (stream == nullptr) return moc_launch(d_zv, d_dmoc, moc.ws_int, g.s_compute);
     return moc_launch(d_zv, d_dmoc, moc.ws_ext, (cudaStream_t)stream);
+}
+
+int cdfmoc_gpu_maxmoc(int slot, int basin, int ijmin, int ijmax, int ikmin, int ikmax, float *ovt, int *loc)
+{
+    REQUIRE_INIT();
+    REQUIRE(moc.ready, CDFGPU_ERR_STATE, "cdfmoc_gpu_maxmoc: cdfmoc_gpu_setup has not been called");
+    REQUIRE(slot >= 0 && slot < g.nslots && ovt && loc, CDFGPU_ERR_ARG, "cdfmoc_gpu_maxmoc: bad argument");
+    REQUIRE(basin >= 0 && basin < moc.nb, CDFGPU_ERR_ARG, "cdfmoc_gpu_maxmoc: basin out of range");
+    REQUIRE(ijmin >= 1 && ijmax <= moc.ny && ijmin <= ijmax && ikmin >= 1 && ikmax <= moc.nz && ikmin <= ikmax,
+            CDFGPU_ERR_ARG, "cdfmoc_gpu_maxmoc: empty or out-of-range window");
+    Slot &s = moc.slots[slot];
+    REQUIRE(s.used, CDFGPU_ERR_STATE, "cdfmoc_gpu_maxmoc: nothing was submitted on this slot");
+    if (!moc.d_ext) CDF_CUDA(cudaMalloc(&moc.d_ext, 4 * sizeof(float)));
+    CDF_CUDA(cudaStreamWaitEvent(g.s_d2h, s.ev_k1, 0));
+    const int nj = ijmax - ijmin + 1, nk = ikmax - ikmin + 1;
+    moc_window_extrema_kernel<<<1, 256, 0, g.s_d2h>>>(s.d_out, moc.ny, moc.nb, basin, ijmin - 1, nj, ikmin - 1, nk,
+                                                     moc.d_ext, reinterpret_cast<int *>(moc.d_ext + 2));
+    CDF_CUDA(cudaGetLastError());
+    ++g.launches;
+    float h[4];
+    CDF_CUDA(cudaMemcpyAsync(h, moc.d_ext, sizeof(h), cudaMemcpyDeviceToHost, g.s_d2h));
+    CDF_CUDA(cudaStreamSynchronize(g.s_d2h));
+    int il[2];
+    memcpy(il, h + 2, sizeof(il));
+    ovt[0] = h[0]; ovt[1] = h[1];
+    loc[0] = il[0] % nj + ijmin; loc[1] = il[0] / nj + ikmin;
+    loc[2] = il[1] % nj + ijmin; loc[3] = il[1] / nj + ikmin;
+    return CDFGPU_OK;
 }
 
 int cdfmoc_gpu_kernel_ms(int slot, float *ms)

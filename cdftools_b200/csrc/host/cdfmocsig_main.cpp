@@ -2,7 +2,7 @@
 // Same options and rules (exactly three mandatory arguments -v -t and -r|-ntr; the default bins are used unless
 // ALL of -sigmin -sigstp -nbins are given, cdfmocsig.f90:237,265), same auxiliary files, same output variables.
 // The loop nest cdfmocsig.f90:366-475 (missing-value scrub, area, EOS, bin, scatter-add, bin cumsum) is one fused
-// kernel per record behind cdfmocsig_gpu_submit / cdfmocsig_gpu_fetch.  Not in this twin: -isodep (:423-454).
+// kernel per record behind cdfmocsig_gpu_submit / cdfmocsig_gpu_fetch; -isodep (:423-469) adds the zoiso* variables.
 #include "host_common.hpp"
 
 using namespace cdfhost;
@@ -46,7 +46,6 @@ int main(int argc, char **argv)
     bool lchk = false;   // cdfmocsig.f90:218-224
     for (const std::string *f : {&cn.fhgr, &cn.fzgr, &cn.fmsk, &cf_vfil, &cf_tfil, &cf_sfil}) lchk = chkfile(*f) || lchk;
     if (lchk) stop(99);
-    if (lisodep) { printf(" ERROR : -isodep is not part of the GPU hot path yet; use the Fortran host for it.\n"); stop(99); }
 
     nc3::Reader vf, tf, sf;
     nc_check(vf.open(cf_vfil), vf.err);
@@ -111,6 +110,9 @@ int main(int argc, char **argv)
     std::vector<OutVar> ovars;
     for (int b = 0; b < nb; ++b)
         ovars.push_back({std::string("zomsf") + bn[b], std::string("Meridional_Overt.Cell_") + ln[b], "Sverdrup", -1000.f, 1000.f});
+    if (lisodep)   // cdfmocsig.f90:537-574
+        for (int b = 0; b < nb; ++b)
+            ovars.push_back({std::string("zoiso") + bn[b], std::string("Zonal_mean_isopycnal_depth_") + ln[b], "m", 0.f, 8000.f});
     std::vector<double> tim(npt, 0.0);
     { const int it = vf.find_var(cn.vtimec); if (it >= 0) for (int r = 0; r < npt; ++r) vf.read_f64(vf.vars[it], r, 0, 1, &tim[r]); }
     OutFile out;
@@ -120,6 +122,11 @@ int main(int argc, char **argv)
     gpu_check(cdfgpu_init(-1, 3), "cdfgpu_init");
     gpu_check(cdfmocsig_gpu_setup(nx, ny, nz, nb, nbins, sigmin, sigstp, pref, eos, e1v.data(), lvvl ? nullptr : e3v.data(),
                                   ibmask.data(), zspv, zspt, zsps, 0, ny), "cdfmocsig_gpu_setup");
+    if (lisodep) {   // gdep(:) = -getvare3(cn_fzgr, cn_gdept, npk) is formed inside the library (cdfmocsig.f90:328)
+        std::vector<float> gdept(nz);
+        read_1d(zgr.nc, zgr.name1d("gdept"), nz, gdept.data());
+        gpu_check(cdfmocsig_gpu_set_isodep(gdept.data()), "cdfmocsig_gpu_set_isodep");
+    }
     // the GPU byte swap applies to every field of a record, so it is used only when all of them are plain float32
     bool raw = vf.is_plain_f32(var_or_die(vf, cn.vomecrty)) && tf.is_plain_f32(var_or_die(tf, cn.votemper)) &&
                sf.is_plain_f32(var_or_die(sf, cn.vosaline));
@@ -140,6 +147,13 @@ int main(int argc, char **argv)
         for (int b = 0; b < nb; ++b) {
             for (int n = 0; n < nbins; ++n) for (int j = 0; j < ny; ++j) plane[(size_t)n * ny + j] = (float)dmoc[((size_t)j * nbins + n) * nb + b];
             out.put(b, jt, plane.data());
+        }
+        if (lisodep) {
+            gpu_check(cdfmocsig_gpu_fetch_isodep(slot, dmoc.data()), "cdfmocsig_gpu_fetch_isodep");
+            for (int b = 0; b < nb; ++b) {
+                for (int n = 0; n < nbins; ++n) for (int j = 0; j < ny; ++j) plane[(size_t)n * ny + j] = (float)dmoc[((size_t)j * nbins + n) * nb + b];
+                out.put(nb + b, jt, plane.data());
+            }
         }
     };
     for (int jt = 0; jt < npt; ++jt) {   // :361

@@ -236,6 +236,35 @@ __global__ void __launch_bounds__(kMocThreads, MINB) moc_zonal_scan_kernel(const
     }
 }
 
+// cdfmaxmoc epilogue (src/cdfmaxmoc.f90:158-167): extrema of REAL(psi(basin, ijmin:ijmax, ikmin:ikmax)) and their
+// first location in Fortran array order.  One CTA; res = {max, min} as float bits, loc = {idx of max, idx of min}.
+__global__ void moc_window_extrema_kernel(const double *__restrict__ psi, int ny, int nb, int basin, int j0, int nj,
+                                          int k0, int nk, float *__restrict__ res, int *__restrict__ loc)
+{
+    __shared__ float s_max[256], s_min[256];
+    __shared__ int s_imax[256], s_imin[256];
+    float vmax = -INFINITY, vmin = INFINITY;
+    int imax = 0x7fffffff, imin = 0x7fffffff;
+    for (int t = threadIdx.x; t < nj * nk; t += blockDim.x) {
+        const int kk = t / nj, jj = t - kk * nj;
+        const float v = (float)psi[((size_t)(k0 + kk) * ny + (j0 + jj)) * nb + basin];
+        if (v > vmax) { vmax = v; imax = t; }
+        if (v < vmin) { vmin = v; imin = t; }
+    }
+    s_max[threadIdx.x] = vmax; s_imax[threadIdx.x] = imax; s_min[threadIdx.x] = vmin; s_imin[threadIdx.x] = imin;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            const float a = s_max[threadIdx.x + o]; const int ia = s_imax[threadIdx.x + o];
+            if (a > s_max[threadIdx.x] || (a == s_max[threadIdx.x] && ia < s_imax[threadIdx.x])) { s_max[threadIdx.x] = a; s_imax[threadIdx.x] = ia; }
+            const float b = s_min[threadIdx.x + o]; const int ib = s_imin[threadIdx.x + o];
+            if (b < s_min[threadIdx.x] || (b == s_min[threadIdx.x] && ib < s_imin[threadIdx.x])) { s_min[threadIdx.x] = b; s_imin[threadIdx.x] = ib; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { res[0] = s_max[0]; res[1] = s_min[0]; loc[0] = s_imax[0]; loc[1] = s_imin[0]; }
+}
+
 // setup kernel: area = fl32(e1v * e3m) for levels 0..nz-2; flags non-finite products.
 __global__ void moc_prep_area_kernel(const float *__restrict__ e1v, const float *__restrict__ e3m,
                                      float *__restrict__ area, size_t nxy, int *nonfinite)

@@ -44,6 +44,8 @@ struct SigParams {
     const float *__restrict__ area;                                    // (nz-1, ny, nx) fl32(e1v*e3v)
     const uint32_t *__restrict__ patw;                                 // [4][ny][pitchw] pattern bytes, shifted copies
     double *__restrict__ out;                                          // (ny, nbins, nb)
+    double *__restrict__ out_iso;                                      // -isodep: (ny, nbins, nb) mean isopycnal depth
+    const float *__restrict__ gdep;                                    // -isodep: -gdept(k), (nz)
     int *tickets;                                                      // [2]
     int nx, ny, nz, nb, nbins, npat, npat1, pitchw;  // npat incl. the all-zero pattern; npat1 = max(npat-1,1)
     int parity;
@@ -269,14 +271,15 @@ struct SigStage {
     uint8_t slot[8 * 32];   // compacted entry -> c*32+lane
 };
 
-template <int EOS, bool SIGMA0>
+template <int EOS, bool SIGMA0, bool ISO>
 __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(const SigParams p)
 {
     extern __shared__ double s_mem[];
     const int nwarps = blockDim.x >> 5, nthreads = blockDim.x;     // chosen by the host so that shared memory fits
     const int hsize = p.nbins * p.npat1;                            // one private histogram
-    double *hist_all = s_mem;                                       // [nwarps][nbins][npat1]
-    double *comb = hist_all + (size_t)nwarps * hsize;            // [nbins][nb]
+    constexpr int NH = ISO ? 3 : 1;                                  // histograms per warp: transport [, depth*area, area]
+    double *hist_all = s_mem;                                       // [nwarps][NH][nbins][npat1]
+    double *comb = hist_all + (size_t)nwarps * NH * hsize;        // [nbins][nb]
     SigStage *stage_all = reinterpret_cast<SigStage *>(comb + (((size_t)p.nbins * p.nb + 1) & ~(size_t)1));  // 16-B aligned
     unsigned *s_poison = reinterpret_cast<unsigned *>(stage_all + nwarps);  // [nbins]
     __shared__ int s_ticket[2];
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nzm1 = p.nz - 1;
     const uint64_t pol = make_evict_first_policy();
-    double *hist = hist_all + (size_t)warp * hsize;
+    double *hist = hist_all + (size_t)warp * NH * hsize;
     SigStage &st = stage_all[warp];
     const int NV = (p.nx + 6) >> 2;                 // vectors per row, upper bound over the 4 alignments
     const int wpr = (NV + kSigWinVec - 1) / kSigWinVec;  // windows per (level) row
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
     if (tid == 0) s_ticket[0] = atomicAdd(ticket, 1);
     int tsel = 0;
     for (;;) {
-        for (int t = tid; t < nwarps * hsize; t += nthreads) hist_all[t] = 0.0;
+        for (int t = tid; t < nwarps * NH * hsize; t += nthreads) hist_all[t] = 0.0;
         for (int t = tid; t < p.nbins; t += nthreads) s_poison[t] = 0u;
         __syncthreads();
         const int j = s_ticket[tsel];
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
                 const int v0 = win * kSigWinVec + 2 * lane;   // this lane's two consecutive vectors = 8 cells
                 uint32_t pw0 = 0xffffffffu, pw1 = 0xffffffffu;
                 unsigned need = 0u;                            // bit c: cell c needs a bin (contributes)
-                float tt[8], ss[8], pr[8];
+                float tt[8], ss[8], pr[8], ar[ISO ? 8 : 1];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) pr[c] = 0.0f;
                 // ---- phase A: load, transport, which cells contribute -----------------------------------------
@@ -350,12 +353,15 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
                         pr[6] = sig_transport(p, vb.z, eb.z, ab.z); pr[7] = sig_transport(p, vb.w, eb.w, ab.w);
                         tt[0] = ta.x; tt[1] = ta.y; tt[2] = ta.z; tt[3] = ta.w; tt[4] = tb.x; tt[5] = tb.y; tt[6] = tb.z; tt[7] = tb.w;
                         ss[0] = sa.x; ss[1] = sa.y; ss[2] = sa.z; ss[3] = sa.w; ss[4] = sb.x; ss[5] = sb.y; ss[6] = sb.z; ss[7] = sb.w;
+                        if (ISO) { ar[0] = aa.x; ar[1] = aa.y; ar[2] = aa.z; ar[3] = aa.w; ar[4] = ab.x; ar[5] = ab.y; ar[6] = ab.z; ar[7] = ab.w; }
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
                             const uint32_t pat = ((c < 4 ? pw0 : pw1) >> (8 * (c & 3))) & 255u;
                             const bool finite = (__float_as_uint(pr[c]) & 0x7f800000u) != 0x7f800000u;
-                            // excluded cell, exact zero, or finite transport not covered by any basin: contributes nothing
-                            if (pat != 255u && pr[c] != 0.0f && (pat != 0u || !finite)) need |= 1u << c;
+                            // excluded cell, exact zero, or finite transport not covered by any basin: contributes nothing.
+                            // With -isodep every covered cell carries area weight into its bin, whatever its transport.
+                            if (ISO ? (pat != 255u && (pat != 0u || (!finite && pr[c] != 0.0f)))
+                                    : (pat != 255u && pr[c] != 0.0f && (pat != 0u || !finite))) need |= 1u << c;
                         }
                     }
                 }
@@ -388,11 +394,11 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
                     // (bin,pattern) neighbours merged (a run's sum travels to its last cell), then the surviving entries
                     // are flushed to the warp's private histogram (hist_flush is a warp collective) ----------------
                     int key[8];
-                    double val[8];
+                    bool mocadd[8];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         key[c] = -1;
-                        val[c] = 0.0;
+                        mocadd[c] = false;
                         if (need & (1u << c)) {
                             const uint32_t pat = ((c < 4 ? pw0 : pw1) >> (8 * (c & 3))) & 255u;
                             const int ib = st.bin[c * 32 + lane];
@@ -407,21 +413,39 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
                                 if (bits) atomicOr(s_poison + (ib - 1), bits);
                                 add = !(pr[c] != pr[c] || pat == 0u);  // an Inf with a covering basin still accumulates
                             }
-                            if (add) {
-                                key[c] = (ib - 1) * p.npat1 + (int)pat - 1;
-                                val[c] = 0.0 - (double)pr[c];
-                            }
+                            mocadd[c] = add;
+                            if (add || (ISO && pat != 0u)) key[c] = (ib - 1) * p.npat1 + (int)pat - 1;
                         }
                     }
+                    // one pass per histogram: values of the 8 cells, run merge (a run's sum travels to its last cell),
+                    // flush of the surviving entries (hist_flush is a warp collective)
+                    auto pass = [&](double *h, auto value_of) {
+                        int kk[8];
+                        double val[8];
 #pragma unroll
-                    for (int c = 1; c < 8; ++c)
-                        if (key[c] == key[c - 1] && key[c] >= 0) {
-                            val[c] += val[c - 1];
-                            key[c - 1] = -1;
-                        }
+                        for (int c = 0; c < 8; ++c) { kk[c] = key[c]; val[c] = (key[c] >= 0) ? value_of(c) : 0.0; }
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        if (__any_sync(kFull, key[c] >= 0)) hist_flush(hist, key[c], val[c], lane);
+                        for (int c = 1; c < 8; ++c)
+                            if (kk[c] == kk[c - 1] && kk[c] >= 0) {
+                                val[c] += val[c - 1];
+                                kk[c - 1] = -1;
+                            }
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            if (__any_sync(kFull, kk[c] >= 0)) hist_flush(h, kk[c], val[c], lane);
+                    };
+                    pass(hist, [&](int c) { return mocadd[c] ? 0.0 - (double)pr[c] : 0.0; });
+                    if (ISO) {   // cdfmocsig.f90:427-428: gdep(jk)*itmask*zarea and itmask*zarea, REAL(4) chains
+                        const float gk = p.gdep[k];
+                        pass(hist + hsize, [&](int c) {
+                            const float itm = (scrub(ss[c], p.sps) == p.sps) ? 0.0f : 1.0f;
+                            return (double)__fmul_rn(__fmul_rn(gk, itm), ar[c]);
+                        });
+                        pass(hist + 2 * hsize, [&](int c) {
+                            const float itm = (scrub(ss[c], p.sps) == p.sps) ? 0.0f : 1.0f;
+                            return (double)__fmul_rn(itm, ar[c]);
+                        });
+                    }
                 }
                 k += nwarps;
                 while (k >= nzm1) { k -= nzm1; ++win; }
@@ -429,19 +453,27 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
         }
         __syncthreads();
         // private histograms -> one (fixed order: deterministic), patterns -> basins, /1e6, poison handling
-        for (int t = tid; t < p.nbins * p.nb; t += nthreads) {
-            const int bin = t / p.nb, b = t - bin * p.nb;
+        auto combine = [&](int which, int bin, int b) {
             double h = 0.0;
             for (int q = 1; q < p.npat; ++q) {
                 const double wgt = c_patw[q][b];
                 if (wgt != 0.0) {
                     double hq = 0.0;
-                    for (int w = 0; w < nwarps; ++w) hq += hist_all[(size_t)w * hsize + bin * p.npat1 + q - 1];
+                    for (int w = 0; w < nwarps; ++w) hq += hist_all[((size_t)w * NH + which) * hsize + bin * p.npat1 + q - 1];
                     h += hq * wgt;
                 }
             }
+            return h;
+        };
+        for (int t = tid; t < p.nbins * p.nb; t += nthreads) {
+            const int bin = t / p.nb, b = t - bin * p.nb;
+            double h = combine(0, bin, b);
             if ((s_poison[bin] >> b) & 1u) h = __longlong_as_double(0x7ff8000000000000LL);  // NaN transport
             comb[t] = h / 1.0e6;
+            if (ISO) {   // depi = depi / wdep where wdep /= 0, else rp_spval (cdfmocsig.f90:463-469); no cumsum
+                const double d = combine(1, bin, b), w = combine(2, bin, b);
+                p.out_iso[(size_t)j * p.nbins * p.nb + t] = (w != 0.0) ? d / w : 99999.0;
+            }
         }
         __syncthreads();
         if (tid < p.nb) {  // integrate from the densest bin, sequentially as the reference does (:472-475)

@@ -36,12 +36,15 @@ SIGNATURES = {
     "cdfmoc_gpu_fetch": (C.c_int, [C.c_int, C.c_void_p]),
     "cdfmoc_gpu_compute_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "cdfmoc_gpu_kernel_ms": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
+    "cdfmoc_gpu_maxmoc": (C.c_int, [C.c_int] * 6 + [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "cdfmoc_gpu_teardown": (C.c_int, []),
     "cdfmocsig_gpu_setup": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                       C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
                                       C.c_int, C.c_int]),
     "cdfmocsig_gpu_submit": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cdfmocsig_gpu_fetch": (C.c_int, [C.c_int, C.c_void_p]),
+    "cdfmocsig_gpu_set_isodep": (C.c_int, [C.c_void_p]),
+    "cdfmocsig_gpu_fetch_isodep": (C.c_int, [C.c_int, C.c_void_p]),
     "cdfmocsig_gpu_compute_device": (C.c_int, [C.c_void_p] * 7),
     "cdfmocsig_gpu_bins_device": (C.c_int, [C.c_void_p] * 4),
     "cdfmocsig_gpu_kernel_ms": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
@@ -181,6 +184,27 @@ def cdfmoc_kernel_ms(slot: int) -> float:
     return ms.value
 
 
+def maxmoc_window(rlat, gdepw, latmin, latmax, depmin, depmax):
+    """Index window of cdfmaxmoc (src/cdfmaxmoc.f90:145-155): the LAST index whose latitude / depth is <= the limit.
+    rlat (ny,) and gdepw (nz,) as cdfmaxmoc holds them (gdepw = -depthw of the file, positive down).  1-based."""
+    ijmin = ijmax = ikmin = ikmax = 0
+    for jj, v in enumerate(rlat, 1):
+        if v <= latmin: ijmin = jj
+        if v <= latmax: ijmax = jj
+    for jk, v in enumerate(gdepw, 1):
+        if v <= depmin: ikmin = jk
+        if v <= depmax: ikmax = jk
+    return ijmin, ijmax, ikmin, ikmax
+
+
+def cdfmoc_maxmoc(slot, basin, ijmin, ijmax, ikmin, ikmax):
+    """-> (ovtmax, ovtmin, (jj,jk) of max, (jj,jk) of min), 1-based, on the slot's device slab."""
+    ovt = (C.c_float * 2)()
+    loc = (C.c_int * 4)()
+    _chk(load().cdfmoc_gpu_maxmoc(slot, basin, ijmin, ijmax, ikmin, ikmax, ovt, loc), "cdfmoc_gpu_maxmoc")
+    return ovt[0], ovt[1], (loc[0], loc[1]), (loc[2], loc[3])
+
+
 def cdfmoc_teardown():
     _chk(load().cdfmoc_gpu_teardown(), "cdfmoc_gpu_teardown")
 
@@ -208,6 +232,16 @@ def cdfmocsig_submit(slot, jt, zv, zt, zs, zveiv=None, e3v_vvl=None):
 
 def cdfmocsig_fetch(slot, out):
     _chk(load().cdfmocsig_gpu_fetch(slot, _ptr(out)), "cdfmocsig_gpu_fetch")
+    return out
+
+
+def cdfmocsig_set_isodep(gdept):
+    _chk(load().cdfmocsig_gpu_set_isodep(_ptr(None if gdept is None else np.ascontiguousarray(gdept, np.float32))),
+         "cdfmocsig_gpu_set_isodep")
+
+
+def cdfmocsig_fetch_isodep(slot, out):
+    _chk(load().cdfmocsig_gpu_fetch_isodep(slot, _ptr(out)), "cdfmocsig_gpu_fetch_isodep")
     return out
 
 

@@ -87,6 +87,11 @@ int cdfmoc_gpu_submit(int slot, int jt, const float *zv);
 int cdfmoc_gpu_fetch(int slot, double *dmoc);
 int cdfmoc_gpu_compute_device(const float *d_zv, double *d_dmoc, void *stream);
 int cdfmoc_gpu_kernel_ms(int slot, float *ms); /* device time of the slot's last kernel, CUDA events */
+/* Optional epilogue on the slot's streamfunction slab: the window extrema cdfmaxmoc computes from moc.nc
+ * (src/cdfmaxmoc.f90:158-167).  Values are taken as REAL(4) (what the file holds); window bounds are 1-based
+ * inclusive indices as found by cdfmaxmoc.f90:145-155; MAXLOC/MINLOC tie rule = first in (j fastest, k) order.
+ * ovt[0..1] = max, min (Sv); loc[0..3] = jj of max, jk of max, jj of min, jk of min (1-based). */
+int cdfmoc_gpu_maxmoc(int slot, int basin, int ijmin, int ijmax, int ikmin, int ikmax, float *ovt, int *loc);
 int cdfmoc_gpu_teardown(void);
 
 /* ---- cdfmocsig: density-space MOC -------------------------------------------------------------------------
@@ -110,6 +115,11 @@ int cdfmocsig_gpu_setup(int nx, int ny, int nz, int nb, int nbins, float sigmin,
 int cdfmocsig_gpu_submit(int slot, int jt, const float *zv, const float *zt, const float *zs, const float *zveiv,
                          const float *e3v_vvl);
 int cdfmocsig_gpu_fetch(int slot, double *dmoc);
+/* -isodep (src/cdfmocsig.f90:319-322,423-430,444-454,463-469): zonal mean of the isopycnal depths.
+ * set_isodep(gdept(nz)) after setup enables it for the following submits (NULL switches it off); fetch_isodep gives
+ * depi(nb,nbins,ny) in metres (negative down, as the reference's gdep = -gdept), 99999. where a class is empty. */
+int cdfmocsig_gpu_set_isodep(const float *gdept);
+int cdfmocsig_gpu_fetch_isodep(int slot, double *depi);
 int cdfmocsig_gpu_compute_device(const float *d_zv, const float *d_zt, const float *d_zs, const float *d_zveiv,
                                  const float *d_e3v_vvl, double *d_dmoc, void *stream);
 int cdfmocsig_gpu_bins_device(const float *d_zt, const float *d_zs, int32_t *d_ibin, void *stream);

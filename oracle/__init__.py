@@ -151,3 +151,28 @@ def cdfmocsig_output(dmoc):
     d = np.ascontiguousarray(dmoc, np.float64)
     lib().oracle_cdfmocsig_output(ny, nb, nbins, _p(d, C.c_double), _p(out, C.c_float))
     return out
+
+
+def maxmoc(rmoc, ijmin, ijmax, ikmin, ikmax):
+    """rmoc (nz, ny) float32 -> (ovtmax, ovtmin, (jj,jk)max, (jj,jk)min), 1-based (cdfmaxmoc.f90:158-167)."""
+    r = _f32(rmoc)
+    ovt = (C.c_float * 2)()
+    loc = (C.c_int * 4)()
+    lib().oracle_maxmoc(r.shape[1], _p(r, C.c_float), ijmin, ijmax, ikmin, ikmax, ovt, loc)
+    return ovt[0], ovt[1], (loc[0], loc[1]), (loc[2], loc[3])
+
+
+def cdfmocsig_record_isodep(e1v, e3v, ibmask, gdept, zv, zt, zs, spv, spt, sps, pref, eos, sigmin, sigstp, nbins):
+    """-> (dmoc, depi), both (ny, nbins, nb) float64.  cdfmocsig.f90:366-475 with -isodep (:423-469)."""
+    e1v, e3v, zv, zt, zs, gdept = (_f32(x) for x in (e1v, e3v, zv, zt, zs, gdept))
+    ibmask = np.ascontiguousarray(ibmask, np.int16)
+    nzm1, ny, nx = zv.shape
+    nb = ibmask.shape[2]
+    out = np.empty((ny, nbins, nb), np.float64)
+    depi = np.empty((ny, nbins, nb), np.float64)
+    lib().oracle_cdfmocsig_record_isodep(nx, ny, nzm1 + 1, nb, int(nbins), C.c_float(sigmin), C.c_float(sigstp),
+                                         C.c_float(pref), int(eos), _p(e1v, C.c_float), _p(e3v, C.c_float),
+                                         _p(ibmask, C.c_int16), C.c_float(spv), C.c_float(spt), C.c_float(sps),
+                                         _p(gdept, C.c_float), _p(zv, C.c_float), _p(zt, C.c_float), _p(zs, C.c_float),
+                                         _p(out, C.c_double), _p(depi, C.c_double))
+    return out, depi

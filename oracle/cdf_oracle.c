@@ -380,3 +380,73 @@ void oracle_cdfmocsig_output(int ny, int nb, int nbins, const double *dmoc, floa
             for (int j = 0; j < ny; ++j)
                 out[((size_t)b * nbins + bin) * ny + j] = (float)dmoc[((size_t)j * nbins + bin) * nb + b];
 }
+
+/* cdfmaxmoc -- src/cdfmaxmoc.f90:158-167: MAXVAL/MINVAL/MAXLOC/MINLOC of rmoc(1,ijmin:ijmax,ikmin:ikmax), REAL(4)
+ * values as read from moc.nc; first occurrence in array order (jj fastest).  Indices 1-based inclusive.
+ * rmoc[k][j] float32.  out: ovt[2] = max,min ; loc[4] = jj,jk of max, jj,jk of min. */
+void oracle_maxmoc(int ny, const float *rmoc, int ijmin, int ijmax, int ikmin, int ikmax, float *ovt, int *loc)
+{
+    float vmax = -INFINITY, vmin = INFINITY;
+    for (int k = ikmin; k <= ikmax; ++k)
+        for (int j = ijmin; j <= ijmax; ++j) {
+            const float v = rmoc[(size_t)(k - 1) * ny + (j - 1)];
+            if (v > vmax) { vmax = v; loc[0] = j; loc[1] = k; }
+            if (v < vmin) { vmin = v; loc[2] = j; loc[3] = k; }
+        }
+    ovt[0] = vmax; ovt[1] = vmin;
+}
+
+/* -isodep -- src/cdfmocsig.f90:423-430,444-454,463-469: zonal-mean depth of the isopycnals.
+ *   depi_tmp(ib,ji) += gdep(jk) * itmask(ji,jj) * zarea(ji,jj)      (REAL(4) chain, added into REAL(8))
+ *   wdep_tmp(ib,ji) +=            itmask(ji,jj) * zarea(ji,jj)
+ *   depi(b,bin,jj)  += depi_tmp(bin,ji) * ibmask(b,ji,jj) ; same for wdep ; i = 2..nx-1, j = 2..ny-1
+ * One level: accumulates into depi/wdep (ny,nbins,nb).  gdepk = -gdept(jk) (cdfmocsig.f90:328). */
+void oracle_isodep_level_accum(int nx, int ny, int nb, int nbins, float gdepk, const float *zarea, const int16_t *itmask,
+                               const int32_t *ibin, const int16_t *ibmask, double *depi, double *wdep)
+{
+    int ij1 = 1, ij2 = ny - 2;
+    if (ny <= 1) { ij1 = 0; ij2 = 0; }
+    for (int j = ij1; j <= ij2; ++j)
+        for (int i = 1; i <= nx - 2; ++i) {
+            size_t c = (size_t)j * nx + i;
+            int ib = ibin[c] - 1;
+            float a = gdepk * (float)itmask[c];
+            a = a * zarea[c];
+            float w = (float)itmask[c] * zarea[c];
+            for (int b = 0; b < nb; ++b) {
+                size_t o = ((size_t)j * nbins + ib) * nb + b;
+                depi[o] += (double)a * (double)ibmask[c * nb + b];
+                wdep[o] += (double)w * (double)ibmask[c * nb + b];
+            }
+        }
+}
+
+/* Whole record with -isodep: returns both the MOC (as oracle_cdfmocsig_record) and depi (ny,nbins,nb), already
+ * divided by wdep where wdep /= 0 and set to 99999. elsewhere (cdfmocsig.f90:463-469). */
+void oracle_cdfmocsig_record_isodep(int nx, int ny, int nz, int nb, int nbins, float sigmin, float sigstp, float pref,
+                                    int eos, const float *e1v, const float *e3v, const int16_t *ibmask, float zspv,
+                                    float zspt, float zsps, const float *gdept, const float *zv_in, const float *zt_in,
+                                    const float *zs_in, double *dmoc, double *depi)
+{
+    size_t n = (size_t)nx * ny;
+    float *zv = malloc(4 * n), *zt = malloc(4 * n), *zs = malloc(4 * n), *zarea = malloc(4 * n);
+    int16_t *itmask = malloc(2 * n);
+    int32_t *ibin = malloc(4 * n);
+    double *dens = malloc(8 * n);
+    size_t no = (size_t)nb * nbins * ny;
+    double *wdep = calloc(no, 8);
+    memset(dmoc, 0, 8 * no);
+    memset(depi, 0, 8 * no);
+    for (int k = 0; k < nz - 1; ++k) {
+        memcpy(zv, zv_in + k * n, 4 * n);
+        memcpy(zt, zt_in + k * n, 4 * n);
+        memcpy(zs, zs_in + k * n, 4 * n);
+        oracle_mocsig_level_prep(nx, ny, zv, zt, zs, NULL, e1v, e3v + k * n, zspv, zspt, zsps, pref, eos, sigmin, sigstp,
+                                 nbins, zarea, itmask, ibin, dens);
+        oracle_mocsig_level_accum(nx, ny, nb, nbins, zv, zarea, ibin, ibmask, 0, dmoc);
+        oracle_isodep_level_accum(nx, ny, nb, nbins, -gdept[k], zarea, itmask, ibin, ibmask, depi, wdep);
+    }
+    for (size_t o = 0; o < no; ++o) depi[o] = (wdep[o] != 0.0) ? depi[o] / wdep[o] : 99999.0;
+    oracle_mocsig_cumsum(ny, nb, nbins, dmoc);
+    free(zv); free(zt); free(zs); free(zarea); free(itmask); free(ibin); free(dens); free(wdep);
+}

@@ -182,3 +182,25 @@ def cdfmocsig_record(e1v, e3v, ibmask, zv, zt, zs, spv, spt, sps, pref, eos, sig
     for b in range(nbins - 2, -1, -1):
         H[:, b, :] = H[:, b + 1, :] + H[:, b, :] / 1.0e6
     return H, bins
+
+
+def isodep_record(e1v, e3v, ibmask, gdept, zt, zs, spt, sps, pref, eos, sigmin, sigstp, nbins):
+    """cdfmocsig.f90:423-430,444-454,463-469 -> depi (ny,nbins,nb) f64 (mean isopycnal depth, 99999. where empty)."""
+    nzm1, ny, nx = zt.shape
+    nb = ibmask.shape[2]
+    D = np.zeros((ny, nbins, nb)); W = np.zeros((ny, nbins, nb))
+    j1, j2 = (1, ny - 2) if ny > 1 else (0, 0)
+    for k in range(nzm1):
+        t = np.where(zt[k] == np.float32(spt), np.float32(0), zt[k]).astype(np.float32)
+        s = np.where(zs[k] == np.float32(sps), np.float32(0), zs[k]).astype(np.float32)
+        area = (e1v * e3v[k]).astype(np.float32)
+        ib, itm, _ = mocsig_bins(t, s, sps, pref, eos, sigmin, sigstp, nbins)
+        gd = np.float32(-np.float32(gdept[k]))
+        a = ((gd * itm.astype(np.float32)).astype(np.float32) * area).astype(np.float32).astype(np.float64)
+        w = (itm.astype(np.float32) * area).astype(np.float32).astype(np.float64)
+        for j in range(j1, j2 + 1):
+            for i in range(1, nx - 1):
+                D[j, ib[j, i] - 1, :] += a[j, i] * ibmask[j, i, :].astype(np.float64)
+                W[j, ib[j, i] - 1, :] += w[j, i] * ibmask[j, i, :].astype(np.float64)
+    with np.errstate(all="ignore"):
+        return np.where(W != 0.0, D / np.where(W != 0.0, W, 1.0), 99999.0)

@@ -104,3 +104,20 @@ def test_cdfmocsig_cli_eiv(tools, oracle_mod, tmp_path):
     f = netcdf_file(str(tmp_path / "sig_eiv.nc"), "r", mmap=False)
     assert np.allclose(f.variables["zomsfglo"][1, :, :, 0], oracle_mod.cdfmocsig_output(H)[0], rtol=2e-7, atol=1e-6)
     f.close()
+
+
+def test_cdfmocsig_cli_isodep(tools, oracle_mod, tmp_path):
+    m = synth.make_mesh("SMALL")
+    ncfiles.write_mesh(m, tmp_path)
+    vrec = ncfiles.write_gridv(m, tmp_path / "gridV.nc", 2)
+    tsrec = ncfiles.write_gridt(m, tmp_path / "gridT.nc", 2)
+    _run(tools["cdfmocsig_gpu"], ["-v", "gridV.nc", "-t", "gridT.nc", "-r", "2000", "-isodep"], tmp_path)
+    ib = oracle_mod.basin_masks(*synth.basin_mask_inputs(m))
+    f = netcdf_file(str(tmp_path / "mocsig.nc"), "r", mmap=False)
+    assert f.variables["zoisoglo"].units == b"m"
+    for r in range(2):
+        H, D = oracle_mod.cdfmocsig_record_isodep(m.e1v, m.e3v_0, ib, m.gdept_1d, vrec[r][:-1], tsrec[r][0][:-1],
+                                                  tsrec[r][1][:-1], 0.0, 0.0, 0.0, 2000.0, 0, 30.0, 0.05, 158)
+        assert np.allclose(f.variables["zomsfatl"][r, :, :, 0], oracle_mod.cdfmocsig_output(H)[1], rtol=2e-7, atol=1e-6)
+        assert np.allclose(f.variables["zoisopac"][r, :, :, 0], oracle_mod.cdfmocsig_output(D)[4], rtol=2e-7, atol=1e-4)
+    f.close()
