@@ -9,6 +9,7 @@
 #include "moc_kernel.cuh"
 #include "moc_kernel_tma.cuh"
 #include "mocsig_kernel.cuh"
+#include "moc_decomp.cuh"
 
 namespace cdfgpu {
 
@@ -38,6 +39,25 @@ struct Slot {
     bool used = false;
     int jt = -1;
 };
+
+// The polynomial-EOS coefficient table lives in one __constant__ symbol shared by cdfmocsig and cdfmoc -decomp; it is
+// (re)loaded, stream-ordered, whenever the launching plan wants the other coefficient set.
+static int g_eos_loaded = -1;   // -1 none, 0 EOS80, 1 TEOS10
+static EosConst g_eos_host;
+static int ensure_eos(int teos10, cudaStream_t st)
+{
+    if (g_eos_loaded == teos10) return CDFGPU_OK;
+    CDF_CUDA(cudaStreamSynchronize(st));   // g_eos_host must not be rewritten under a pending copy
+    memcpy(g_eos_host.c, teos10 ? CDF_TEOS10_COEF : CDF_EOS80_COEF, sizeof(g_eos_host.c));
+    memcpy(g_eos_host.r0, CDF_EOS_R0, sizeof(g_eos_host.r0));
+    g_eos_host.rdeltaS = teos10 ? CDF_TEOS10_RDELTAS : CDF_EOS80_RDELTAS;
+    g_eos_host.r1_S0 = teos10 ? CDF_TEOS10_R1_S0 : CDF_EOS80_R1_S0;
+    CDF_CUDA(cudaDeviceSynchronize());     // no kernel of any stream may still read the old table
+    CDF_CUDA(cudaMemcpyToSymbolAsync(c_eos, &g_eos_host, sizeof(g_eos_host), 0, cudaMemcpyHostToDevice, st));
+    CDF_CUDA(cudaStreamSynchronize(st));
+    g_eos_loaded = teos10;
+    return CDFGPU_OK;
+}
 
 static int swap_record(float *d, size_t n, cudaStream_t st)
 {
@@ -121,6 +141,14 @@ struct MocPlan {
     int16_t *d_ibmask = nullptr;
     int *d_flag = nullptr;
     float *d_ext = nullptr;   // cdfmaxmoc epilogue result
+    // -decomp (cdfmoc.f90:390-517)
+    bool decomp = false;
+    int dec_teos10 = 0;
+    float *d_e1u = nullptr, *d_zcoef = nullptr, *d_zt = nullptr, *d_zs = nullptr, *d_sig = nullptr, *d_hdep = nullptr,
+          *d_zvgeo = nullptr;
+    int16_t *d_umask = nullptr, *d_tmask = nullptr;
+    double *d_dvbt = nullptr, *d_dvgeo = nullptr, *d_sh = nullptr, *d_bt = nullptr, *d_ag = nullptr, *d_btw = nullptr;
+    std::vector<double> dec_dlh, dec_dlref;
     Workspace ws_int, ws_ext;
     Slot slots[CDFGPU_MAX_SLOTS];
     int grid = 0;
@@ -212,9 +240,9 @@ static int moc_launch_t(const MocParams &p, cudaStream_t st)
     return moc_launch_v<NB, 4, 3>(p, st);
 }
 
-static int moc_launch(const float *d_zv, double *d_out, Workspace &ws, cudaStream_t st)
+static int moc_launch(const float *d_zv, double *d_out, Workspace &ws, cudaStream_t st, int noscan = 0)
 {
-    if (!moc.general && moc.nclass > 0 && moc.use_tma) {  // TMA-fed class-sum kernel
+    if (!noscan && !moc.general && moc.nclass > 0 && moc.use_tma) {  // TMA-fed class-sum kernel
         MocTmaParams t;
         t.zv = d_zv; t.area = moc.d_area; t.classes = moc.d_classes; t.ibmask = moc.d_ibmask; t.out = d_out;
         t.tickets = ws.d_tickets; t.col_done = ws.d_col;
@@ -246,6 +274,7 @@ static int moc_launch(const float *d_zv, double *d_out, Workspace &ws, cudaStrea
     p.parity = ws.parity;
     p.chunk = moc.chunk;
     p.general = moc.general;
+    p.noscan = noscan;
     ws.parity ^= 1;
     switch (moc.nb) {
     case 1: return moc_launch_t<1>(p, st);
@@ -272,6 +301,28 @@ static int moc_build_area()
     CDF_CUDA(cudaMemcpyAsync(&flag, moc.d_flag, sizeof(int), cudaMemcpyDeviceToHost, g.s_compute));
     CDF_CUDA(cudaStreamSynchronize(g.s_compute));
     if (flag) moc.general = 1;
+    return CDFGPU_OK;
+}
+
+template <int NB>
+static void decomp_weighted_t(const double *w, double *raw, cudaStream_t st)
+{
+    decomp_weighted_rows_kernel<NB><<<g.sm_count * 4, 256, 0, st>>>(moc.d_area, moc.d_ibmask, w, moc.nx, moc.ny, moc.nz - 1, raw);
+}
+static int decomp_weighted(const double *w, double *raw, cudaStream_t st)
+{
+    switch (moc.nb) {
+    case 1: decomp_weighted_t<1>(w, raw, st); break;
+    case 2: decomp_weighted_t<2>(w, raw, st); break;
+    case 3: decomp_weighted_t<3>(w, raw, st); break;
+    case 4: decomp_weighted_t<4>(w, raw, st); break;
+    case 5: decomp_weighted_t<5>(w, raw, st); break;
+    case 6: decomp_weighted_t<6>(w, raw, st); break;
+    case 7: decomp_weighted_t<7>(w, raw, st); break;
+    default: decomp_weighted_t<8>(w, raw, st); break;
+    }
+    CDF_CUDA(cudaGetLastError());
+    ++g.launches;
     return CDFGPU_OK;
 }
 
@@ -400,6 +451,9 @@ int cdfmoc_gpu_teardown(void)
     if (g.inited) cdfgpu_synchronize();
     cudaFree(moc.d_e1v); cudaFree(moc.d_e3m); cudaFree(moc.d_area); cudaFree(moc.d_maskw);
     cudaFree(moc.d_ibmask); cudaFree(moc.d_flag); cudaFree(moc.d_classes); cudaFree(moc.d_ext);
+    cudaFree(moc.d_e1u); cudaFree(moc.d_zcoef); cudaFree(moc.d_zt); cudaFree(moc.d_zs); cudaFree(moc.d_sig);
+    cudaFree(moc.d_hdep); cudaFree(moc.d_zvgeo); cudaFree(moc.d_umask); cudaFree(moc.d_tmask); cudaFree(moc.d_dvbt);
+    cudaFree(moc.d_dvgeo); cudaFree(moc.d_sh); cudaFree(moc.d_bt); cudaFree(moc.d_ag); cudaFree(moc.d_btw);
     free_ws(moc.ws_int); free_ws(moc.ws_ext);
     for (auto &s : moc.slots) free_slot(s);
     moc = MocPlan();
@@ -564,6 +618,116 @@ int cdfmoc_gpu_maxmoc(int slot, int basin, int ijmin, int ijmax, int ikmin, int 
     ovt[0] = h[0]; ovt[1] = h[1];
     loc[0] = il[0] % nj + ijmin; loc[1] = il[0] / nj + ikmin;
     loc[2] = il[1] % nj + ijmin; loc[3] = il[1] / nj + ikmin;
+    return CDFGPU_OK;
+}
+
+int cdfmoc_gpu_decomp_setup(int teos10, const float *e1u, const float *gphiv, const float *gdept, const int16_t *umask,
+                            const int16_t *tmask)
+{
+    REQUIRE_INIT();
+    REQUIRE(moc.ready, CDFGPU_ERR_STATE, "cdfmoc_gpu_decomp_setup: cdfmoc_gpu_setup has not been called");
+    REQUIRE(e1u && gphiv && gdept && umask && tmask, CDFGPU_ERR_ARG, "cdfmoc_gpu_decomp_setup: null pointer");
+    const size_t nxy = (size_t)moc.nx * moc.ny, n3 = nxy * (size_t)(moc.nz - 1), nout = moc.out_elems();
+    // f at the V point and -g/rau0/f (cdfmoc.f90:425-433), REAL(4), with libm's sinf like the Fortran run-time
+    std::vector<float> zcoef(nxy);
+    {
+        const float rau0 = 1025.0f, grav = 9.81f;
+        const float rpi = acosf(-1.f);
+        for (size_t c = 0; c < nxy; ++c) {
+            volatile float f = 2 * 2 * rpi;
+            f = f / (24.0f * 3600.f);
+            volatile float a = rpi * gphiv[c];
+            a = a / 180.0f;
+            f = f * sinf(a);
+            if (f != 0.f) { volatile float gg = -grav / rau0; zcoef[c] = gg / f; } else zcoef[c] = 0.f;
+        }
+    }
+    // reference profile at every level's depth (eos.f90:843-845), plain double arithmetic on the host
+    moc.dec_dlh.resize(moc.nz); moc.dec_dlref.resize(moc.nz);
+    for (int k = 0; k < moc.nz; ++k) {
+        const double *R = CDF_EOS_R0;
+        volatile double h = (double)gdept[k] * 1.e-4;
+        volatile double a = R[5] * h;
+        a = a + R[4]; a = a * h; a = a + R[3]; a = a * h; a = a + R[2]; a = a * h; a = a + R[1]; a = a * h;
+        a = a + R[0]; a = a * h;
+        moc.dec_dlh[k] = h; moc.dec_dlref[k] = a;
+    }
+    moc.dec_teos10 = teos10 ? 1 : 0;
+#define DALLOC(p, n) if (!(p)) CDF_CUDA(cudaMalloc(&(p), (n)))
+    DALLOC(moc.d_e1u, nxy * 4); DALLOC(moc.d_zcoef, nxy * 4); DALLOC(moc.d_zt, n3 * 4); DALLOC(moc.d_zs, n3 * 4);
+    DALLOC(moc.d_sig, nxy * 4); DALLOC(moc.d_hdep, nxy * 4); DALLOC(moc.d_zvgeo, n3 * 4 + 16);
+    DALLOC(moc.d_umask, n3 * 2); DALLOC(moc.d_tmask, n3 * 2); DALLOC(moc.d_dvbt, nxy * 8); DALLOC(moc.d_dvgeo, 2 * nxy * 8);
+    DALLOC(moc.d_sh, nout * 8); DALLOC(moc.d_bt, nout * 8); DALLOC(moc.d_ag, nout * 8); DALLOC(moc.d_btw, nout * 8);
+#undef DALLOC
+    CDF_CUDA(cudaMemcpyAsync(moc.d_e1u, e1u, nxy * 4, cudaMemcpyHostToDevice, g.s_compute));
+    CDF_CUDA(cudaMemcpyAsync(moc.d_zcoef, zcoef.data(), nxy * 4, cudaMemcpyHostToDevice, g.s_compute));
+    CDF_CUDA(cudaMemcpyAsync(moc.d_umask, umask, n3 * 2, cudaMemcpyHostToDevice, g.s_compute));
+    CDF_CUDA(cudaMemcpyAsync(moc.d_tmask, tmask, n3 * 2, cudaMemcpyHostToDevice, g.s_compute));
+    CDF_CUDA(cudaStreamSynchronize(g.s_compute));
+    moc.decomp = true;
+    return CDFGPU_OK;
+}
+
+int cdfmoc_gpu_decomp_submit(int slot, int jt, const float *zv, const float *zt, const float *zs)
+{
+    REQUIRE_INIT();
+    REQUIRE(moc.ready && moc.decomp, CDFGPU_ERR_STATE, "cdfmoc_gpu_decomp_submit: cdfmoc_gpu_decomp_setup has not been called");
+    REQUIRE(zt && zs, CDFGPU_ERR_ARG, "cdfmoc_gpu_decomp_submit: null pointer");
+    int rc = cdfmoc_gpu_submit(slot, jt, zv);   // total MOC (cdfmoc.f90:352-388) into the slot's slab
+    if (rc) return rc;
+    rc = ensure_eos(moc.dec_teos10, g.s_compute);
+    if (rc) return rc;
+    cudaStream_t st = g.s_compute;
+    Slot &s = moc.slots[slot];
+    const int nx = moc.nx, ny = moc.ny, nz = moc.nz, nzm1 = nz - 1;
+    const size_t nxy = (size_t)nx * ny, n3 = nxy * (size_t)nzm1, nout = moc.out_elems();
+    const int gsz = g.sm_count * 8;
+    CDF_CUDA(cudaMemcpyAsync(moc.d_zt, zt, n3 * 4, cudaMemcpyHostToDevice, st));
+    CDF_CUDA(cudaMemcpyAsync(moc.d_zs, zs, n3 * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = swap_record(moc.d_zt, n3, st)) || (rc = swap_record(moc.d_zs, n3, st))) return rc;
+    // 2.1 barotropic: vertical mean of V, weighted zonal sums, integration (:397-419)
+    decomp_vbar_kernel<<<gsz, 256, 0, st>>>(moc.d_e3m, s.d_in[0], nxy, nzm1, 0, moc.d_hdep, 1, moc.d_dvbt);
+    if ((rc = decomp_weighted(moc.d_dvbt, moc.d_bt, st))) return rc;
+    decomp_scan_kernel<<<(ny * moc.nb + 127) / 128, 128, 0, st>>>(moc.d_bt, nullptr, ny * moc.nb, nz);
+    // 2.2 geostrophic shear: level by level from the bottom (:435-478)
+    CDF_CUDA(cudaMemsetAsync(moc.d_dvgeo, 0, 2 * nxy * 8, st));
+    int iup = 0, ido = 1;
+    for (int k = nzm1 - 1; k >= 0; --k) {
+        decomp_sigma_kernel<<<gsz, 256, 0, st>>>(moc.d_zt + (size_t)k * nxy, moc.d_zs + (size_t)k * nxy,
+                                                 moc.d_tmask + (size_t)k * nxy, moc.dec_dlh[k], moc.dec_dlref[k], nxy, moc.d_sig);
+        decomp_geo_level_kernel<<<gsz, 256, 0, st>>>(moc.d_sig, moc.d_umask + (size_t)k * nxy, moc.d_e1u, moc.d_zcoef,
+                                                     moc.d_ibmask, moc.nb, moc.d_e3m + (size_t)k * nxy,
+                                                     s.d_in[0] + (size_t)(nzm1 - 1) * nxy, moc.d_dvgeo + (size_t)ido * nxy,
+                                                     moc.d_dvgeo + (size_t)iup * nxy, moc.d_zvgeo + (size_t)k * nxy, nx, ny);
+        std::swap(iup, ido);
+        g.launches += 2;
+    }
+    CDF_CUDA(cudaGetLastError());
+    // zonal sums of the geostrophic velocity (K1 without its scan), its pseudo-barotropic part, integration (:464-510)
+    if ((rc = moc_launch(moc.d_zvgeo, moc.d_sh, moc.ws_int, st, 1))) return rc;
+    decomp_vbar_kernel<<<gsz, 256, 0, st>>>(moc.d_e3m, moc.d_zvgeo, nxy, nzm1, 1, moc.d_hdep, 0, moc.d_dvbt);
+    if ((rc = decomp_weighted(moc.d_dvbt, moc.d_btw, st))) return rc;
+    decomp_scan_kernel<<<(ny * moc.nb + 127) / 128, 128, 0, st>>>(moc.d_sh, moc.d_btw, ny * moc.nb, nz);
+    // 2.3 ageostrophic (:516)
+    decomp_ageo_kernel<<<gsz, 256, 0, st>>>(s.d_out, moc.d_sh, moc.d_bt, moc.d_ag, nout);
+    CDF_CUDA(cudaGetLastError());
+    g.launches += 5;
+    CDF_CUDA(cudaEventRecord(s.ev_k1, st));
+    return CDFGPU_OK;
+}
+
+int cdfmoc_gpu_decomp_fetch(int slot, double *dmoc, double *dmoc_sh, double *dmoc_bt, double *dmoc_ag)
+{
+    REQUIRE_INIT();
+    REQUIRE(moc.ready && moc.decomp, CDFGPU_ERR_STATE, "cdfmoc_gpu_decomp_fetch: cdfmoc_gpu_decomp_setup has not been called");
+    REQUIRE(dmoc && dmoc_sh && dmoc_bt && dmoc_ag, CDFGPU_ERR_ARG, "cdfmoc_gpu_decomp_fetch: null pointer");
+    int rc = cdfmoc_gpu_fetch(slot, dmoc);
+    if (rc) return rc;
+    const size_t nb8 = moc.out_elems() * sizeof(double);
+    CDF_CUDA(cudaMemcpyAsync(dmoc_sh, moc.d_sh, nb8, cudaMemcpyDeviceToHost, g.s_d2h));
+    CDF_CUDA(cudaMemcpyAsync(dmoc_bt, moc.d_bt, nb8, cudaMemcpyDeviceToHost, g.s_d2h));
+    CDF_CUDA(cudaMemcpyAsync(dmoc_ag, moc.d_ag, nb8, cudaMemcpyDeviceToHost, g.s_d2h));
+    CDF_CUDA(cudaStreamSynchronize(g.s_d2h));
     return CDFGPU_OK;
 }
 

@@ -35,6 +35,7 @@ struct MocParams {
     int parity;                         // launch parity selecting tickets[parity]
     int chunk;                          // consecutive levels of one column handed out per ticket
     int general;                        // 1: masks are not 0/1 (or area not finite) -> literal chain everywhere
+    int noscan;                         // 1: leave the raw zonal sums in `out` (-decomp combines before integrating)
 };
 
 constexpr int kMocThreads = 256;
@@ -213,7 +214,9 @@ __global__ void __launch_bounds__(kMocThreads, MINB) moc_zonal_scan_kernel(const
             done = old + (k1 - k0);
         }
         done = __shfl_sync(kFull, done, 0);
-        if (done == nzm1) {
+        if (done == nzm1 && p.noscan) {
+            if (lane == 0) p.col_done[j] = 0;
+        } else if (done == nzm1) {
             asm volatile("fence.acq_rel.gpu;" ::: "memory");
             double *sc = s_scan + (size_t)warp * nzm1 * NB;
             for (int t = lane; t < nzm1 * NB; t += kWarp) {

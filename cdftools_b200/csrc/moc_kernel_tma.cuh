@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256, 1) moc_zonal_scan_tma_kernel(const MocTma
                     MocParams g;   // literal chain for this row (NaN/Inf semantics of the reference)
                     g.zv = p.zv; g.area = p.area; g.maskw = nullptr; g.ibmask = p.ibmask; g.out = p.out;
                     g.tickets = nullptr; g.col_done = nullptr;
-                    g.nx = p.nx; g.ny = p.ny; g.nz = p.nz; g.pitchw = 0; g.parity = 0; g.chunk = 1; g.general = 1;
+                    g.nx = p.nx; g.ny = p.ny; g.nz = p.nz; g.pitchw = 0; g.parity = 0; g.chunk = 1; g.general = 1; g.noscan = 0;
                     row_general_store<NB>(g, j, k, lane);
                 } else if (lane < NB) {
                     p.out[((size_t)k * p.ny + j) * NB + lane] = 0.0 - tb;

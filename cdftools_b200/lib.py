@@ -37,6 +37,9 @@ SIGNATURES = {
     "cdfmoc_gpu_compute_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "cdfmoc_gpu_kernel_ms": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
     "cdfmoc_gpu_maxmoc": (C.c_int, [C.c_int] * 6 + [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "cdfmoc_gpu_decomp_setup": (C.c_int, [C.c_int] + [C.c_void_p] * 5),
+    "cdfmoc_gpu_decomp_submit": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cdfmoc_gpu_decomp_fetch": (C.c_int, [C.c_int] + [C.c_void_p] * 4),
     "cdfmoc_gpu_teardown": (C.c_int, []),
     "cdfmocsig_gpu_setup": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                       C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
@@ -182,6 +185,25 @@ def cdfmoc_kernel_ms(slot: int) -> float:
     ms = C.c_float()
     _chk(load().cdfmoc_gpu_kernel_ms(slot, C.byref(ms)), "cdfmoc_gpu_kernel_ms")
     return ms.value
+
+
+def cdfmoc_decomp_setup(e1u, gphiv, gdept, umask, tmask, teos10=False):
+    """umask, tmask: int16 (>= nz-1, ny, nx) planes as the reference reads them (cdfmoc.f90:439-440)."""
+    assert umask.dtype == np.int16 and tmask.dtype == np.int16 and e1u.dtype == np.float32
+    _chk(load().cdfmoc_gpu_decomp_setup(int(teos10), _ptr(e1u), _ptr(np.ascontiguousarray(gphiv, np.float32)),
+                                        _ptr(np.ascontiguousarray(gdept, np.float32)), _ptr(umask), _ptr(tmask)),
+         "cdfmoc_gpu_decomp_setup")
+
+
+def cdfmoc_decomp_submit(slot, jt, zv, zt, zs):
+    _chk(load().cdfmoc_gpu_decomp_submit(slot, jt, _ptr(zv), _ptr(zt), _ptr(zs)), "cdfmoc_gpu_decomp_submit")
+
+
+def cdfmoc_decomp_fetch(slot, shape):
+    outs = {k: np.empty(shape, np.float64) for k in ("total", "sh", "bt", "ag")}
+    _chk(load().cdfmoc_gpu_decomp_fetch(slot, _ptr(outs["total"]), _ptr(outs["sh"]), _ptr(outs["bt"]), _ptr(outs["ag"])),
+         "cdfmoc_gpu_decomp_fetch")
+    return outs
 
 
 def maxmoc_window(rlat, gdepw, latmin, latmax, depmin, depmax):

@@ -92,6 +92,16 @@ int cdfmoc_gpu_kernel_ms(int slot, float *ms); /* device time of the slot's last
  * inclusive indices as found by cdfmaxmoc.f90:145-155; MAXLOC/MINLOC tie rule = first in (j fastest, k) order.
  * ovt[0..1] = max, min (Sv); loc[0..3] = jj of max, jk of max, jj of min, jk of min (1-based). */
 int cdfmoc_gpu_maxmoc(int slot, int basin, int ijmin, int ijmax, int ikmin, int ikmax, float *ovt, int *loc);
+/* -decomp (src/cdfmoc.f90:290-304,353,360-365,390-517): barotropic / geostrophic-shear / ageostrophic split.
+ * decomp_setup (after cdfmoc_gpu_setup): e1u, gphiv (nx,ny); gdept (nz); umask, tmask (nx,ny,nz-1 levels used) as the
+ *   INTEGER(2) planes the reference reads level by level (:439-440); teos10 selects the EOS of sigmai (:443).
+ * decomp_submit: one record of V, T, S (nx,ny,nz-1); computes the total MOC and the three components.
+ * decomp_fetch : dmoc, dmoc_sh, dmoc_bt, dmoc_ag, each (nb,ny,nz) in Sv.  dmoc_sh starts from zero for every record
+ *   (the reference never initialises it, cdfmoc.f90:299,471, which is only meaningful for a single record). */
+int cdfmoc_gpu_decomp_setup(int teos10, const float *e1u, const float *gphiv, const float *gdept, const int16_t *umask,
+                            const int16_t *tmask);
+int cdfmoc_gpu_decomp_submit(int slot, int jt, const float *zv, const float *zt, const float *zs);
+int cdfmoc_gpu_decomp_fetch(int slot, double *dmoc, double *dmoc_sh, double *dmoc_bt, double *dmoc_ag);
 int cdfmoc_gpu_teardown(void);
 
 /* ---- cdfmocsig: density-space MOC -------------------------------------------------------------------------

@@ -176,3 +176,21 @@ def cdfmocsig_record_isodep(e1v, e3v, ibmask, gdept, zv, zt, zs, spv, spt, sps, 
                                          _p(gdept, C.c_float), _p(zv, C.c_float), _p(zt, C.c_float), _p(zs, C.c_float),
                                          _p(out, C.c_double), _p(depi, C.c_double))
     return out, depi
+
+
+def cdfmoc_decomp_record(e1v, e1u, gphiv, gdept, e3m, ibmask, umask, tmask, zv, zt, zs, teos10=False, dmoc_sh_in=None):
+    """cdfmoc -decomp (cdfmoc.f90:390-517) -> dict of (nz,ny,nb) float64 arrays: total, sh, bt, ag."""
+    e1v, e1u, gphiv, gdept, e3m, zv, zt, zs = (_f32(x) for x in (e1v, e1u, gphiv, gdept, e3m, zv, zt, zs))
+    ibmask = np.ascontiguousarray(ibmask, np.int16)
+    um, tm = np.ascontiguousarray(umask, np.int16), np.ascontiguousarray(tmask, np.int16)
+    nz, ny, nx = e3m.shape
+    nb = ibmask.shape[2]
+    outs = {k: np.zeros((nz, ny, nb), np.float64) for k in ("total", "sh", "bt", "ag")}
+    if dmoc_sh_in is not None:
+        outs["sh"][...] = dmoc_sh_in
+    lib().oracle_cdfmoc_decomp_record(nx, ny, nz, nb, int(teos10), _p(e1v, C.c_float), _p(e1u, C.c_float),
+                                      _p(gphiv, C.c_float), _p(gdept, C.c_float), _p(e3m, C.c_float),
+                                      _p(ibmask, C.c_int16), _p(um, C.c_int16), _p(tm, C.c_int16), _p(zv, C.c_float),
+                                      _p(zt, C.c_float), _p(zs, C.c_float), _p(outs["total"], C.c_double),
+                                      _p(outs["sh"], C.c_double), _p(outs["bt"], C.c_double), _p(outs["ag"], C.c_double))
+    return outs

@@ -450,3 +450,133 @@ void oracle_cdfmocsig_record_isodep(int nx, int ny, int nz, int nb, int nbins, f
     oracle_mocsig_cumsum(ny, nb, nbins, dmoc);
     free(zv); free(zt); free(zs); free(zarea); free(itmask); free(ibin); free(dens); free(wdep);
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * cdfmoc -decomp -- src/cdfmoc.f90:353,360-365,390-517.  One time record.
+ * Types as declared in the reference (:101-117): hdep, zcoef, zsig0, zmsv, zv REAL(4); dvbt, dvgeo, dgeo and all
+ * dmoc_* REAL(8).  Inputs: e3m = e3v*vmask (nz,ny,nx); umask, tmask (nz,ny,nx) INTEGER(2); zv, zt, zs levels 1..nz-1;
+ * gphiv (ny,nx); gdept (nz).  dmoc_sh is IN/OUT: the reference never zeroes it (:299,:471) -- pass zeros for npt=1.
+ * Outputs (nz,ny,nb): dmoc (total), dmoc_sh, dmoc_bt, dmoc_ag.  Level nz of every array is left as given/zero.
+ * ------------------------------------------------------------------------------------------- */
+static void zonal_weighted(int nx, int ny, int nz, int nb, const float *e1v, const float *e3m, const int16_t *ibmask,
+                           const double *dvbt, double *out)
+{   /* :403-415 / :490-502: out(b,jj,jk) -= e1v*e3v*ibmask*dvbt  (REAL(4) triple product, REAL(8) last multiply) */
+    for (int k = 0; k < nz - 1; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int b = 0; b < nb; ++b) {
+                double acc = out[((size_t)k * ny + j) * nb + b];
+                for (int i = 0; i < nx; ++i) {
+                    size_t c = (size_t)j * nx + i;
+                    float t = e1v[c] * e3m[(size_t)k * ny * nx + c];
+                    t = t * (float)ibmask[c * nb + b];
+                    acc = acc - (double)t * dvbt[c];
+                }
+                out[((size_t)k * ny + j) * nb + b] = acc;
+            }
+}
+
+void oracle_cdfmoc_decomp_record(int nx, int ny, int nz, int nb, int teos10, const float *e1v, const float *e1u,
+                                 const float *gphiv, const float *gdept, const float *e3m, const int16_t *ibmask,
+                                 const int16_t *umask, const int16_t *tmask, const float *zv_in, const float *zt_in,
+                                 const float *zs_in, double *dmoc, double *dmoc_sh, double *dmoc_bt, double *dmoc_ag)
+{
+    const size_t nxy = (size_t)nx * ny, nout = (size_t)nb * ny * nz;
+    double *dvbt = calloc(nxy, 8), *dvgeo = calloc(2 * nxy, 8), *dmoc_btw = calloc(nout, 8), *dens = malloc(8 * nxy);
+    float *hdep = calloc(nxy, 4), *zcoef = malloc(4 * nxy), *zsig0 = malloc(4 * nxy), *zv = malloc(4 * nxy);
+    /* 1) total MOC + barotropic sums (:352-388, :360-365) */
+    oracle_cdfmoc_record(nx, ny, nz, nb, e1v, e3m, ibmask, zv_in, dmoc);
+    for (int k = 0; k < nz - 1; ++k)
+        for (size_t c = 0; c < nxy; ++c) {
+            float t = e3m[k * nxy + c] * zv_in[k * nxy + c];
+            dvbt[c] = dvbt[c] + (double)t;              /* dvbt + e3v*zv*1.d0 */
+            hdep[c] = hdep[c] + e3m[k * nxy + c];       /* REAL(4) running sum */
+        }
+    memcpy(zv, zv_in + (size_t)(nz - 2) * nxy, 4 * nxy);   /* zv keeps the last level read (:357) */
+    /* 2.1) barotropic (:397-419) */
+    for (size_t c = 0; c < nxy; ++c) dvbt[c] = (hdep[c] != 0.f) ? dvbt[c] / (double)hdep[c] : 0.0;
+    memset(dmoc_bt, 0, 8 * nout);
+    zonal_weighted(nx, ny, nz, nb, e1v, e3m, ibmask, dvbt, dmoc_bt);
+    for (int k = nz - 2; k >= 0; --k)
+        for (size_t o = 0; o < (size_t)ny * nb; ++o)
+            dmoc_bt[(size_t)k * ny * nb + o] = dmoc_bt[(size_t)(k + 1) * ny * nb + o] + dmoc_bt[(size_t)k * ny * nb + o] / 1.0e6;
+    /* 2.2) geostrophic shear (:425-478) */
+    {
+        const float rau0 = 1025.0f, grav = 9.81f;
+        const float rpi = acosf(-1.f);
+        for (size_t c = 0; c < nxy; ++c) {
+            float f = 2 * 2 * rpi;                      /* 2*2*rpi/(24.0*3600.)*SIN(rpi*gphiv/180.0), left to right */
+            f = f / (24.0f * 3600.f);
+            float a = rpi * gphiv[c];
+            a = a / 180.0f;
+            f = f * sinf(a);
+            if (f != 0.f) { float g = -grav / rau0; zcoef[c] = g / f; } else zcoef[c] = 0.f;
+        }
+    }
+    memset(dvbt, 0, 8 * nxy);
+    int iup = 0, ido = 1;
+    for (int k = nz - 2; k >= 0; --k) {
+        const int16_t *um = umask + k * nxy, *tm = tmask + k * nxy;
+        oracle_sigmai_dep(nxy, zt_in + k * nxy, zs_in + k * nxy, gdept[k], teos10, dens);
+        for (size_t c = 0; c < nxy; ++c) zsig0[c] = (float)(dens[c] * (double)tm[c]);
+        for (int j = 1; j <= ny - 2; ++j)
+            for (int i = 1; i <= nx - 2; ++i) {
+                size_t c = (size_t)j * nx + i, cn = c + nx;   /* (ji,jj) and (ji,jj+1) */
+                int16_t su = (int16_t)(um[cn - 1] + um[cn] + um[c - 1] + um[c]);
+                float zmsv = 1.f / (float)(su > 1 ? su : 1);
+                float t1 = (zsig0[cn] - zsig0[cn - 1]) * (float)um[cn - 1]; t1 = t1 / e1u[cn - 1];
+                float t2 = (zsig0[cn + 1] - zsig0[cn]) * (float)um[cn];     t2 = t2 / e1u[cn];
+                float t3 = (zsig0[c] - zsig0[c - 1]) * (float)um[c - 1];    t3 = t3 / e1u[c - 1];
+                float t4 = (zsig0[c + 1] - zsig0[c]) * (float)um[c];        t4 = t4 / e1u[c];
+                float sgeo = t1 + t2; sgeo = sgeo + t3; sgeo = sgeo + t4;
+                double dgeo = (double)sgeo;
+                double d = (double)zcoef[c] * dgeo;
+                d = d * (double)zmsv;
+                d = d * (double)ibmask[c * nb + 0];
+                d = d * (double)e3m[k * nxy + c];
+                dvgeo[iup * nxy + c] = dvgeo[ido * nxy + c] + d;
+                zv[c] = (float)(0.5 * (dvgeo[iup * nxy + c] + dvgeo[ido * nxy + c]));
+            }
+        for (size_t c = 0; c < nxy; ++c) {
+            float t = e3m[k * nxy + c] * zv[c];
+            dvbt[c] = dvbt[c] + (double)t;
+        }
+        for (int j = 0; j < ny; ++j)
+            for (int b = 0; b < nb; ++b) {
+                double acc = dmoc_sh[((size_t)k * ny + j) * nb + b];
+                for (int i = 0; i < nx; ++i) {
+                    size_t c = (size_t)j * nx + i;
+                    float t = e1v[c] * e3m[k * nxy + c];
+                    t = t * (float)ibmask[c * nb + b];
+                    t = t * zv[c];
+                    acc = acc - (double)t;
+                }
+                dmoc_sh[((size_t)k * ny + j) * nb + b] = acc;
+            }
+        int tmp = iup; iup = ido; ido = tmp;
+    }
+    for (size_t c = 0; c < nxy; ++c) dvbt[c] = (hdep[c] != 0.f) ? dvbt[c] / (double)hdep[c] : 0.0;
+    /* 2.2.1) pseudo-barotropic part of the shear (:489-505) */
+    zonal_weighted(nx, ny, nz, nb, e1v, e3m, ibmask, dvbt, dmoc_btw);
+    for (size_t o = 0; o < nout; ++o) dmoc_sh[o] = dmoc_sh[o] - dmoc_btw[o];
+    for (int k = nz - 2; k >= 0; --k)
+        for (size_t o = 0; o < (size_t)ny * nb; ++o)
+            dmoc_sh[(size_t)k * ny * nb + o] = dmoc_sh[(size_t)(k + 1) * ny * nb + o] + dmoc_sh[(size_t)k * ny * nb + o] / 1.0e6;
+    /* 2.3) ageostrophic (:516) */
+    for (size_t o = 0; o < nout; ++o) dmoc_ag[o] = dmoc[o] - dmoc_sh[o] - dmoc_bt[o];
+    free(dvbt); free(dvgeo); free(dmoc_btw); free(dens); free(hdep); free(zcoef); free(zsig0); free(zv);
+}
+
+/* zcoef of :428-433 alone (the host computes it with libm's sinf, exactly as the Fortran run-time does) */
+void oracle_decomp_zcoef(size_t n, const float *gphiv, float *zcoef)
+{
+    const float rau0 = 1025.0f, grav = 9.81f;
+    const float rpi = acosf(-1.f);
+    for (size_t c = 0; c < n; ++c) {
+        float f = 2 * 2 * rpi;
+        f = f / (24.0f * 3600.f);
+        float a = rpi * gphiv[c];
+        a = a / 180.0f;
+        f = f * sinf(a);
+        if (f != 0.f) { float g = -grav / rau0; zcoef[c] = g / f; } else zcoef[c] = 0.f;
+    }
+}

@@ -204,3 +204,88 @@ def isodep_record(e1v, e3v, ibmask, gdept, zt, zs, spt, sps, pref, eos, sigmin, 
                 W[j, ib[j, i] - 1, :] += w[j, i] * ibmask[j, i, :].astype(np.float64)
     with np.errstate(all="ignore"):
         return np.where(W != 0.0, D / np.where(W != 0.0, W, 1.0), 99999.0)
+
+
+def _sinf(x32):
+    """libm's sinf, element by element: the value the Fortran run-time's REAL(4) SIN gives on this platform."""
+    import ctypes
+    libm = ctypes.CDLL("libm.so.6")
+    libm.sinf.restype, libm.sinf.argtypes = ctypes.c_float, [ctypes.c_float]
+    flat = np.asarray(x32, np.float32).ravel()
+    uniq, inv = np.unique(flat, return_inverse=True)
+    vals = np.array([libm.sinf(float(u)) for u in uniq], np.float32)
+    return vals[inv].reshape(np.shape(x32))
+
+
+def cdfmoc_decomp_record(e1v, e1u, gphiv, gdept, e3m, ibmask, umask, tmask, zv, zt, zs, teos10=False):
+    """cdfmoc -decomp, src/cdfmoc.f90:390-517 (vectorised restatement; zonal sums via sequential cumsum)."""
+    f4, f8 = np.float32, np.float64
+    nz, ny, nx = e3m.shape
+    nb = ibmask.shape[2]
+    mf = ibmask.astype(f4)
+    total = cdfmoc_record(e1v, e3m, ibmask, zv)
+
+    def weighted(dv):
+        out = np.zeros((nz, ny, nb))
+        for k in range(nz - 1):
+            a = (e1v * e3m[k]).astype(f4)
+            for b in range(nb):
+                t = (a * mf[:, :, b]).astype(f4).astype(f8) * dv
+                out[k, :, b] = -np.cumsum(t, axis=1)[:, -1]
+        return out + 0.0
+
+    def scan(d):
+        d = d.copy()
+        for k in range(nz - 2, -1, -1):
+            d[k] = d[k + 1] + d[k] / 1.0e6
+        return d
+
+    dvbt = np.zeros((ny, nx)); hdep = np.zeros((ny, nx), f4)
+    for k in range(nz - 1):
+        dvbt = dvbt + (e3m[k] * zv[k]).astype(f4).astype(f8)
+        hdep = (hdep + e3m[k]).astype(f4)
+    with np.errstate(all="ignore"):
+        dvbt = np.where(hdep != 0, dvbt / np.where(hdep != 0, hdep, 1).astype(f8), 0.0)
+    bt = scan(weighted(dvbt))
+
+    rpi = f4(np.arccos(f4(-1.0)))
+    f = f4(f4(4.0) * rpi) / f4(f4(24.0) * f4(3600.0))
+    ang = ((rpi * gphiv.astype(f4)).astype(f4) / f4(180.0)).astype(f4)
+    fcor = (f4(f) * _sinf(ang)).astype(f4)
+    g = f4(f4(-9.81) / f4(1025.0))
+    with np.errstate(all="ignore"):
+        zcoef = np.where(fcor != 0, (g / np.where(fcor != 0, fcor, 1)).astype(f4), f4(0)).astype(f4)
+
+    dvgeo = np.zeros((2, ny, nx)); dvbt = np.zeros((ny, nx)); sh = np.zeros((nz, ny, nb))
+    zvg = zv[nz - 2].astype(f4).copy()          # border cells keep the last level read by the first loop
+    iup, ido = 0, 1
+    J, I = slice(1, ny - 1), slice(1, nx - 1)
+    for k in range(nz - 2, -1, -1):
+        um = umask[k].astype(np.int16); umf = um.astype(f4)
+        sig = (sigmai_dep(zt[k], zs[k], gdept[k], teos10) * tmask[k].astype(f8)).astype(f4)
+        su = (um[2:, 0:-2] + um[2:, 1:-1] + um[1:-1, 0:-2] + um[1:-1, 1:-1]).astype(np.int16)
+        zmsv = (f4(1.0) / np.maximum(su, 1).astype(f4)).astype(f4)
+        def term(sa, sb, u, e):   # ((sa - sb) * real(u)) / e  in REAL(4)
+            return (((sa - sb).astype(f4) * u).astype(f4) / e).astype(f4)
+        t1 = term(sig[2:, 1:-1], sig[2:, 0:-2], umf[2:, 0:-2], e1u[2:, 0:-2])
+        t2 = term(sig[2:, 2:], sig[2:, 1:-1], umf[2:, 1:-1], e1u[2:, 1:-1])
+        t3 = term(sig[1:-1, 1:-1], sig[1:-1, 0:-2], umf[1:-1, 0:-2], e1u[1:-1, 0:-2])
+        t4 = term(sig[1:-1, 2:], sig[1:-1, 1:-1], umf[1:-1, 1:-1], e1u[1:-1, 1:-1])
+        dgeo = (((t1 + t2).astype(f4) + t3).astype(f4) + t4).astype(f4).astype(f8)
+        d = zcoef[J, I].astype(f8) * dgeo
+        d = d * zmsv.astype(f8)
+        d = d * ibmask[J, I, 0].astype(f8)
+        d = d * e3m[k][J, I].astype(f8)
+        dvgeo[iup][J, I] = dvgeo[ido][J, I] + d
+        zvg[J, I] = (0.5 * (dvgeo[iup][J, I] + dvgeo[ido][J, I])).astype(f4)
+        dvbt = dvbt + (e3m[k] * zvg).astype(f4).astype(f8)
+        a = (e1v * e3m[k]).astype(f4)
+        for b in range(nb):
+            t = ((a * mf[:, :, b]).astype(f4) * zvg).astype(f4)
+            sh[k, :, b] = -np.cumsum(t.astype(f8), axis=1)[:, -1]
+        iup, ido = ido, iup
+    sh = sh + 0.0
+    with np.errstate(all="ignore"):
+        dvbt = np.where(hdep != 0, dvbt / np.where(hdep != 0, hdep, 1).astype(f8), 0.0)
+    sh = scan(sh - weighted(dvbt))
+    return {"total": total, "sh": sh, "bt": bt, "ag": total - sh - bt}

@@ -106,3 +106,22 @@ def test_sigma_axis_and_default_bins(oracle_mod):
     ax = oracle_mod.sigma_axis(158, 30.0, 0.05)
     assert np.array_equal(ax, npo.sigma_axis(158, 30.0, 0.05))
     assert ax[0] == np.float32(30.0) + np.float32(np.float32(0.5) * np.float32(0.05))
+
+
+@pytest.mark.parametrize("grid", ["TINY", "ODD", "SMALL"])
+def test_decomp_and_isodep_c_vs_numpy_bit_exact(oracle_mod, grid):
+    m = synth.make_mesh(grid)
+    ib, e3m = case_inputs(oracle_mod, m, synth)
+    v = synth.make_v_record(m, 0)[:-1]
+    t, s = (x[:-1] for x in synth.make_ts_record(m, 0))
+    um, tm = m.umask.astype(np.int16), m.tmask.astype(np.int16)
+    a = oracle_mod.cdfmoc_decomp_record(m.e1v, m.e1u, m.gphiv, m.gdept_1d, e3m, ib, um, tm, v, t, s)
+    b = npo.cdfmoc_decomp_record(m.e1v, m.e1u, m.gphiv, m.gdept_1d, e3m, ib, um, tm, v, t, s)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["ag"], a["total"] - a["sh"] - a["bt"])                # cdfmoc.f90:516
+    assert np.array_equal(a["total"], oracle_mod.cdfmoc_record(m.e1v, e3m, ib, v))
+    H, D = oracle_mod.cdfmocsig_record_isodep(m.e1v, m.e3v_0, ib, m.gdept_1d, v, t, s, 0.0, 0.0, 0.0, 2000.0, 0, 30.0, 0.05, 158)
+    assert np.array_equal(D, npo.isodep_record(m.e1v, m.e3v_0, ib, m.gdept_1d, t, s, 0.0, 0.0, 2000.0, 0, 30.0, 0.05, 158))
+    H0, _ = oracle_mod.cdfmocsig_record(m.e1v, m.e3v_0, ib, v, t, s, 0.0, 0.0, 0.0, 2000.0, 0, 30.0, 0.05, 158)
+    assert np.array_equal(H, H0)
