@@ -3,7 +3,8 @@
 // same exit codes (STOP 99: usage / missing file / unknown option; 98: NetCDF; new 97: GPU library error).
 // The hot loop nest cdfmoc.f90:352-388 is replaced by cdfmoc_gpu_submit / cdfmoc_gpu_fetch with a 3-deep record
 // pipeline: record jt+1 is read and sent to the device while record jt is being integrated.
-// Not in this twin: -decomp (cdfmoc.f90:390-517) and -rapid (:598-1004) stay with the Fortran host.
+// -decomp (cdfmoc.f90:390-517) runs on the GPU too (one record in flight); -rapid (:598-1004) stays with the
+// Fortran host (an O(nx*nz) section diagnostic, not part of the hot path).
 #include "host_common.hpp"
 
 using namespace cdfhost;
@@ -48,8 +49,8 @@ int main(int argc, char **argv)
     lchk = chkfile(cf_vfil.empty() ? "(no -v file)" : cf_vfil) || lchk;
     if (ldec || lrap) lchk = chkfile(cf_tfil) || chkfile(cf_sfil) || lchk;
     if (lchk) stop(99);
-    if (ldec || lrap) {
-        printf(" ERROR : -decomp / -rapid are not part of the GPU hot path; use the Fortran host for them.\n");
+    if (lrap) {
+        printf(" ERROR : -rapid is not part of the GPU hot path; use the Fortran host for it.\n");
         stop(99);
     }
 
@@ -96,13 +97,18 @@ int main(int argc, char **argv)
     load_e3v(0);
 
     // output file (CreateOutput, cdfmoc.f90:1006-1188)
-    std::vector<OutVar> ovars = {{"zomsfglo", "Meridional_Overt.Cell_Global", "Sverdrup", -1000.f, 1000.f}};
-    if (lbas) {
-        ovars.push_back({"zomsfatl", "Meridional_Overt.Cell_Atlantic", "Sverdrup", -1000.f, 1000.f});
-        ovars.push_back({"zomsfinp", "Meridional_Overt.Cell_IndoPacif", "Sverdrup", -1000.f, 1000.f});
-        ovars.push_back({"zomsfind", "Meridional_Overt.Cell_Indian", "Sverdrup", -1000.f, 1000.f});
-        ovars.push_back({"zomsfpac", "Meridional_Overt.Cell_pacif", "Sverdrup", -1000.f, 1000.f});
-        ovars.push_back({"zomsfinp0", "Meridional_Overt.Cell_IndPac0", "Sverdrup", -1000.f, 1000.f});
+    // variable order of CreateOutput (cdfmoc.f90:1030-1180): per basin total [, _sh, _bt, _ag], then inp0 likewise
+    const char *vn[6] = {"zomsfglo", "zomsfatl", "zomsfinp", "zomsfind", "zomsfpac", "zomsfinp0"};
+    const char *vl[6] = {"Global", "Atlantic", "IndoPacif", "Indian", "pacif", "IndPac0"};
+    const char *dsuf[3] = {"_sh", "_bt", "_ag"};
+    const char *dlong[3] = {"GeoShear_Merid_StreamFunction", "Barotropic_Merid_StreamFunction", "Ageostoph_Merid_StreamFunction"};
+    std::vector<OutVar> ovars;
+    for (int b = 0; b < (lbas ? 6 : 1); ++b) {
+        ovars.push_back({vn[b], std::string("Meridional_Overt.Cell_") + vl[b], "Sverdrup", -1000.f, 1000.f});
+        if (ldec)
+            for (int d = 0; d < 3; ++d)
+                ovars.push_back({std::string(vn[b]) + dsuf[d], std::string(dlong[d]) + (b ? std::string("_") + vl[b] : ""),
+                                 "Sverdrup", -1000.f, 1000.f});
     }
     std::vector<double> tim(npt, 0.0);
     { const int it = vf.find_var(cn.vtimec); if (it >= 0) for (int r = 0; r < npt; ++r) vf.read_f64(vf.vars[it], r, 0, 1, &tim[r]); }
@@ -116,6 +122,20 @@ int main(int argc, char **argv)
     if (iv < 0) { printf(" ERROR : %s not found in %s\n", cn.vomecrty.c_str(), cf_vfil.c_str()); stop(98); }
     const bool raw = vf.is_plain_f32(vf.vars[iv]);
     gpu_check(cdfgpu_set_input_big_endian(raw ? 1 : 0), "cdfgpu_set_input_big_endian");
+    if (ldec) {   // extra fields of the decomposition (cdfmoc.f90:312-313,439-442)
+        std::vector<float> e1u(nxy), gdept(nz);
+        read_level(hgr, "e1u", 0, 0, nxy, e1u.data());
+        read_1d(zgr.nc, zgr.name1d("gdept"), nz, gdept.data());
+        std::vector<int16_t> um(n3), tm(n3);
+        for (int k = 0; k < nz - 1; ++k) {
+            read_level(msk, "umask", k, 0, nxy, lev.data());
+            for (size_t c = 0; c < nxy; ++c) um[(size_t)k * nxy + c] = (int16_t)lev[c];
+            read_level(msk, "tmask", k, 0, nxy, lev.data());
+            for (size_t c = 0; c < nxy; ++c) tm[(size_t)k * nxy + c] = (int16_t)lev[c];
+        }
+        gpu_check(cdfmoc_gpu_decomp_setup(lteos10 ? 1 : 0, e1u.data(), gphiv.data(), gdept.data(), um.data(), tm.data()),
+                  "cdfmoc_gpu_decomp_setup");
+    }
     Pinned buf0(n3), buf1(n3), buf2(n3);
     float *bufs[3] = {buf0.p, buf1.p, buf2.p};
     std::vector<double> dmoc((size_t)nb * ny * nz);
@@ -134,6 +154,37 @@ int main(int argc, char **argv)
             out.put(nb, jt, plane.data());
         }
     };
+    if (ldec) {   // one record in flight; V, T, S of the record (cdfmoc.f90:357,441-442)
+        nc3::Reader tf, sf;
+        nc_check(tf.open(cf_tfil), tf.err);
+        nc_check(sf.open(cf_sfil), sf.err);
+        bool raw3 = raw && tf.is_plain_f32(tf.vars[std::max(0, tf.find_var(cn.votemper))]) &&
+                    sf.is_plain_f32(sf.vars[std::max(0, sf.find_var(cn.vosaline))]);
+        gpu_check(cdfgpu_set_input_big_endian(raw3 ? 1 : 0), "cdfgpu_set_input_big_endian");
+        std::vector<double> dsh(dmoc.size()), dbt(dmoc.size()), dag(dmoc.size());
+        const std::vector<double> *comp[4] = {&dmoc, &dsh, &dbt, &dag};
+        for (int jt = 0; jt < npt; ++jt) {
+            if (lvvl && jt > 0) { load_e3v(jt); gpu_check(cdfmoc_gpu_set_e3v(e3v.data()), "cdfmoc_gpu_set_e3v"); }
+            read_record(vf, cn.vomecrty, jt, n3, bufs[0], raw3);
+            read_record(tf, cn.votemper, jt, n3, bufs[1], raw3);
+            read_record(sf, cn.vosaline, jt, n3, bufs[2], raw3);
+            gpu_check(cdfmoc_gpu_decomp_submit(0, jt, bufs[0], bufs[1], bufs[2]), "cdfmoc_gpu_decomp_submit");
+            gpu_check(cdfmoc_gpu_decomp_fetch(0, dmoc.data(), dsh.data(), dbt.data(), dag.data()), "cdfmoc_gpu_decomp_fetch");
+            int iv = 0;
+            for (int b = 0; b < (lbas ? 6 : 1); ++b)
+                for (int d = 0; d < 4; ++d, ++iv) {
+                    const std::vector<double> &a = *comp[d];
+                    for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) {
+                        const size_t o = ((size_t)k * ny + j) * nb;
+                        plane[(size_t)k * ny + j] = (b < 5) ? (float)a[o + b] : (float)(a[o + 0] - a[o + 1]);   // inp0 = glo - atl (:549-566)
+                    }
+                    out.put(iv, jt, plane.data());
+                }
+        }
+        out.w.close();
+        gpu_check(cdfgpu_finalize(), "cdfgpu_finalize");
+        return 0;
+    }
     for (int jt = 0; jt < npt; ++jt) {   // cdfmoc.f90:338
         const int slot = lvvl ? 0 : jt % 3;
         if (!lvvl && jt >= 3) drain(slot, jt - 3);

@@ -121,3 +121,22 @@ def test_cdfmocsig_cli_isodep(tools, oracle_mod, tmp_path):
         assert np.allclose(f.variables["zomsfatl"][r, :, :, 0], oracle_mod.cdfmocsig_output(H)[1], rtol=2e-7, atol=1e-6)
         assert np.allclose(f.variables["zoisopac"][r, :, :, 0], oracle_mod.cdfmocsig_output(D)[4], rtol=2e-7, atol=1e-4)
     f.close()
+
+
+def test_cdfmoc_cli_decomp(tools, oracle_mod, tmp_path):
+    m = synth.make_mesh("SMALL")
+    ncfiles.write_mesh(m, tmp_path)
+    vrec = ncfiles.write_gridv(m, tmp_path / "gridV.nc", 2)
+    tsrec = ncfiles.write_gridt(m, tmp_path / "gridT.nc", 2)
+    _run(tools["cdfmoc_gpu"], ["-v", "gridV.nc", "-t", "gridT.nc", "-decomp", "-o", "moc_dec.nc"], tmp_path)
+    ib, e3m = case_inputs(oracle_mod, m, synth)
+    f = netcdf_file(str(tmp_path / "moc_dec.nc"), "r", mmap=False)
+    assert len([n for n in f.variables if n.startswith("zomsf")]) == 24          # nvarout = 4 * nbasinso (cdfmoc.f90:276)
+    for r in range(2):
+        ref = oracle_mod.cdfmoc_decomp_record(m.e1v, m.e1u, m.gphiv, m.gdept_1d, e3m, ib, m.umask.astype(np.int16),
+                                              m.tmask.astype(np.int16), vrec[r][:-1], tsrec[r][0][:-1], tsrec[r][1][:-1])
+        for name, key, b in (("zomsfglo", "total", 0), ("zomsfatl_sh", "sh", 1), ("zomsfpac_bt", "bt", 4), ("zomsfind_ag", "ag", 3)):
+            assert np.allclose(f.variables[name][r, :, :, 0], ref[key][:, :, b].astype(np.float32), rtol=2e-7, atol=1e-6), (r, name)
+        inp0_sh = (ref["sh"][:, :, 0] - ref["sh"][:, :, 1]).astype(np.float32)
+        assert np.allclose(f.variables["zomsfinp0_sh"][r, :, :, 0], inp0_sh, rtol=2e-7, atol=1e-6)
+    f.close()
