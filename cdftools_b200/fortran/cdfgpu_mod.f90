@@ -56,6 +56,12 @@ MODULE cdfgpu
        TYPE(C_PTR), VALUE :: p
      END FUNCTION cdfgpu_pinned_free
 
+     ! records given to *_submit are raw big-endian file bytes: byte swap on the device
+     INTEGER(C_INT) FUNCTION cdfgpu_set_input_big_endian(on) BIND(C, NAME='cdfgpu_set_input_big_endian')
+       IMPORT :: C_INT
+       INTEGER(C_INT), VALUE :: on
+     END FUNCTION cdfgpu_set_input_big_endian
+
      ! ---- cdfmoc ------------------------------------------------------------
      INTEGER(C_INT) FUNCTION cdfmoc_gpu_setup(nx, ny, nz, nb, e1v, e3v, ibmask) BIND(C, NAME='cdfmoc_gpu_setup')
        IMPORT :: C_INT, C_FLOAT, C_INT16_T
@@ -80,6 +86,37 @@ MODULE cdfgpu
        INTEGER(C_INT), VALUE :: slot
        REAL(C_DOUBLE), INTENT(out) :: dmoc(*)                ! (nbasins,npjglo,npk), Sv, integrated
      END FUNCTION cdfmoc_gpu_fetch
+
+     ! cdfmaxmoc window search on the slot's device slab (cdfmaxmoc.f90:158-167)
+     INTEGER(C_INT) FUNCTION cdfmoc_gpu_maxmoc(slot, basin, ijmin, ijmax, ikmin, ikmax, ovt, loc) &
+          &                                    BIND(C, NAME='cdfmoc_gpu_maxmoc')
+       IMPORT :: C_INT, C_FLOAT
+       INTEGER(C_INT), VALUE :: slot, basin, ijmin, ijmax, ikmin, ikmax    ! basin 0-based, window 1-based inclusive
+       REAL(C_FLOAT),  INTENT(out) :: ovt(2)                 ! max, min (Sv)
+       INTEGER(C_INT), INTENT(out) :: loc(4)                 ! jj,jk of max ; jj,jk of min (1-based)
+     END FUNCTION cdfmoc_gpu_maxmoc
+
+     ! -decomp (cdfmoc.f90:390-517)
+     INTEGER(C_INT) FUNCTION cdfmoc_gpu_decomp_setup(teos10, e1u, gphiv, gdept, iumask, itmask) &
+          &                                          BIND(C, NAME='cdfmoc_gpu_decomp_setup')
+       IMPORT :: C_INT, C_FLOAT, C_INT16_T
+       INTEGER(C_INT), VALUE :: teos10
+       REAL(C_FLOAT),      INTENT(in) :: e1u(*), gphiv(*), gdept(*)
+       INTEGER(C_INT16_T), INTENT(in) :: iumask(*), itmask(*)   ! (npiglo,npjglo,npk-1)
+     END FUNCTION cdfmoc_gpu_decomp_setup
+
+     INTEGER(C_INT) FUNCTION cdfmoc_gpu_decomp_submit(slot, jt, zv, zt, zs) BIND(C, NAME='cdfmoc_gpu_decomp_submit')
+       IMPORT :: C_INT, C_FLOAT
+       INTEGER(C_INT), VALUE :: slot, jt
+       REAL(C_FLOAT), INTENT(in) :: zv(*), zt(*), zs(*)
+     END FUNCTION cdfmoc_gpu_decomp_submit
+
+     INTEGER(C_INT) FUNCTION cdfmoc_gpu_decomp_fetch(slot, dmoc, dmoc_sh, dmoc_bt, dmoc_ag) &
+          &                                          BIND(C, NAME='cdfmoc_gpu_decomp_fetch')
+       IMPORT :: C_INT, C_DOUBLE
+       INTEGER(C_INT), VALUE :: slot
+       REAL(C_DOUBLE), INTENT(out) :: dmoc(*), dmoc_sh(*), dmoc_bt(*), dmoc_ag(*)   ! each (nbasins,npjglo,npk)
+     END FUNCTION cdfmoc_gpu_decomp_fetch
 
      INTEGER(C_INT) FUNCTION cdfmoc_gpu_teardown() BIND(C, NAME='cdfmoc_gpu_teardown')
        IMPORT :: C_INT
@@ -109,6 +146,18 @@ MODULE cdfgpu
        INTEGER(C_INT), VALUE :: slot
        REAL(C_DOUBLE), INTENT(out) :: dmoc(*)                ! (nbasins,nbins,npjglo), Sv, integrated
      END FUNCTION cdfmocsig_gpu_fetch
+
+     ! -isodep (cdfmocsig.f90:423-469)
+     INTEGER(C_INT) FUNCTION cdfmocsig_gpu_set_isodep(gdept) BIND(C, NAME='cdfmocsig_gpu_set_isodep')
+       IMPORT :: C_INT, C_FLOAT
+       REAL(C_FLOAT), INTENT(in) :: gdept(*)                 ! (npk), positive depths; the library uses -gdept
+     END FUNCTION cdfmocsig_gpu_set_isodep
+
+     INTEGER(C_INT) FUNCTION cdfmocsig_gpu_fetch_isodep(slot, depi) BIND(C, NAME='cdfmocsig_gpu_fetch_isodep')
+       IMPORT :: C_INT, C_DOUBLE
+       INTEGER(C_INT), VALUE :: slot
+       REAL(C_DOUBLE), INTENT(out) :: depi(*)                ! (nbasins,nbins,npjglo)
+     END FUNCTION cdfmocsig_gpu_fetch_isodep
 
      INTEGER(C_INT) FUNCTION cdfmocsig_gpu_teardown() BIND(C, NAME='cdfmocsig_gpu_teardown')
        IMPORT :: C_INT
