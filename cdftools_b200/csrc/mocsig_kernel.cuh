@@ -56,6 +56,9 @@ struct SigParams {
     double dlh, dlref;
     double inv_sigstp, qmargin;  // fast bin filter: 1/sigstp and the safety distance to a bin edge (q units); <0: off
     double dlref_m1000, nbins_d, half_m_margin;   // dlref - 1000, (double)nbins, 0.5 - qmargin
+    double qoffset;                               // (dlref - 1000 - sigmin) / sigstp
+    size_t patplane;                              // words per pre-shifted pattern plane = ny * pitchw
+    int scrub_ts;                                 // T or S missing value is not zero
 };
 
 // ---- equation of state ----------------------------------------------------------------------------------------
@@ -271,8 +274,597 @@ struct SigStage {
     uint8_t slot[8 * 32];   // compacted entry -> c*32+lane
 };
 
+// One 256-cell window (level k, window `win` of latitude row j), fully general: any mix of covered / uncovered cells,
+// NaN / Inf transports (poison), -isodep.  Cell-granular compaction through the warp's staging area.
 template <int EOS, bool SIGMA0, bool ISO>
-__global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(const SigParams p)
+__device__ __forceinline__ void sig_window_general(const SigParams &p, SigStage &st, double *hist, unsigned *s_poison,
+                                                   int hsize, int j, int k, int win, int lane, uint64_t pol)
+{
+    const size_t e0 = ((size_t)k * p.ny + j) * (size_t)p.nx;
+    const int s = (int)(e0 & 3);
+    const int nvec = (s + p.nx + 3) >> 2;
+    const int v0 = win * kSigWinVec + 2 * lane;   // this lane's two consecutive vectors = 8 cells
+    uint32_t pw0 = 0xffffffffu, pw1 = 0xffffffffu;
+    unsigned need = 0u;                            // bit c: cell c needs a bin (contributes)
+    float tt[8], ss[8], pr[8], ar[ISO ? 8 : 1];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) pr[c] = 0.0f;
+    // ---- phase A: load, transport, which cells contribute -----------------------------------------
+    if (v0 < nvec) {
+        const size_t off = (e0 - s) + 4 * (size_t)v0;
+        const uint32_t *pwp = p.patw + ((size_t)s * p.ny + j) * p.pitchw + v0;
+        const bool two = v0 + 1 < nvec;
+        pw0 = __ldg(pwp);
+        if (two) pw1 = __ldg(pwp + 1);
+        if ((pw0 & pw1) != 0xffffffffu) {
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 *pv = reinterpret_cast<const float4 *>(p.zv + off);
+            const float4 *pa = reinterpret_cast<const float4 *>(p.area + off);
+            const float4 *pt = reinterpret_cast<const float4 *>(p.zt + off);
+            const float4 *ps = reinterpret_cast<const float4 *>(p.zs + off);
+            const float4 va = ld_stream_f4(pv, pol), vb = two ? ld_stream_f4(pv + 1, pol) : z4;
+            const float4 aa = ld_stream_f4(pa, pol), ab = two ? ld_stream_f4(pa + 1, pol) : z4;
+            const float4 ta = ld_stream_f4(pt, pol), tb = two ? ld_stream_f4(pt + 1, pol) : z4;
+            const float4 sa = ld_stream_f4(ps, pol), sb = two ? ld_stream_f4(ps + 1, pol) : z4;
+            float4 ea = z4, eb = z4;
+            if (p.zveiv) {
+                const float4 *pe = reinterpret_cast<const float4 *>(p.zveiv + off);
+                ea = ld_stream_f4(pe, pol);
+                if (two) eb = ld_stream_f4(pe + 1, pol);
+            }
+            pr[0] = sig_transport(p, va.x, ea.x, aa.x); pr[1] = sig_transport(p, va.y, ea.y, aa.y);
+            pr[2] = sig_transport(p, va.z, ea.z, aa.z); pr[3] = sig_transport(p, va.w, ea.w, aa.w);
+            pr[4] = sig_transport(p, vb.x, eb.x, ab.x); pr[5] = sig_transport(p, vb.y, eb.y, ab.y);
+            pr[6] = sig_transport(p, vb.z, eb.z, ab.z); pr[7] = sig_transport(p, vb.w, eb.w, ab.w);
+            tt[0] = ta.x; tt[1] = ta.y; tt[2] = ta.z; tt[3] = ta.w; tt[4] = tb.x; tt[5] = tb.y; tt[6] = tb.z; tt[7] = tb.w;
+            ss[0] = sa.x; ss[1] = sa.y; ss[2] = sa.z; ss[3] = sa.w; ss[4] = sb.x; ss[5] = sb.y; ss[6] = sb.z; ss[7] = sb.w;
+            if (ISO) { ar[0] = aa.x; ar[1] = aa.y; ar[2] = aa.z; ar[3] = aa.w; ar[4] = ab.x; ar[5] = ab.y; ar[6] = ab.z; ar[7] = ab.w; }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t pat = ((c < 4 ? pw0 : pw1) >> (8 * (c & 3))) & 255u;
+                const bool finite = (__float_as_uint(pr[c]) & 0x7f800000u) != 0x7f800000u;
+                // excluded cell, exact zero, or finite transport not covered by any basin: contributes nothing.
+                // With -isodep every covered cell carries area weight into its bin, whatever its transport.
+                if (ISO ? (pat != 255u && (pat != 0u || (!finite && pr[c] != 0.0f)))
+                        : (pat != 255u && pr[c] != 0.0f && (pat != 0u || !finite))) need |= 1u << c;
+            }
+        }
+    }
+    // ---- compaction: the cells that need the EOS, in (lane, c) order, over the whole warp ------------
+    const int mine = __popc(need);
+    int base = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(kFull, base, d);
+        if (lane >= d) base += o;
+    }
+    const int nneed = __shfl_sync(kFull, base, 31);
+    base -= mine;
+    if (nneed > 0) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (need & (1u << c)) {
+                const int e = base + __popc(need & ((1u << c) - 1u));
+                st.ct[e] = tt[c];
+                st.cs[e] = ss[c];
+                st.slot[e] = (uint8_t)(c * 32 + lane);
+            }
+        __syncwarp();
+        // ---- phase B: dense EOS + bin over the compacted list ---------------------------------------
+        for (int e = lane; e < nneed; e += 32)
+            st.bin[st.slot[e]] =
+                (uint16_t)sigma_bin_fast<EOS, SIGMA0>(scrub(st.ct[e], p.spt), scrub(st.cs[e], p.sps), p);
+        __syncwarp();
+        // ---- phase C: the lane's 8 consecutive cells, all in registers: key/value per cell, equal
+        // (bin,pattern) neighbours merged (a run's sum travels to its last cell), then the surviving entries
+        // are flushed to the warp's private histogram (hist_flush is a warp collective) ----------------
+        int key[8];
+        bool mocadd[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            key[c] = -1;
+            mocadd[c] = false;
+            if (need & (1u << c)) {
+                const uint32_t pat = ((c < 4 ? pw0 : pw1) >> (8 * (c & 3))) & 255u;
+                const int ib = st.bin[c * 32 + lane];
+                bool add = true;
+                if ((__float_as_uint(pr[c]) & 0x7f800000u) == 0x7f800000u) {
+                    // NaN/Inf transport: basin b is poisoned iff (0-p)*mask_b is NaN (NaN*x, or Inf*0)
+                    unsigned bits = 0u;
+                    for (int b = 0; b < p.nb; ++b) {
+                        const double cc = __dmul_rn(0.0 - (double)pr[c], c_patw[pat][b]);
+                        if (cc != cc) bits |= 1u << b;
+                    }
+                    if (bits) atomicOr(s_poison + (ib - 1), bits);
+                    add = !(pr[c] != pr[c] || pat == 0u);  // an Inf with a covering basin still accumulates
+                }
+                mocadd[c] = add;
+                if (add || (ISO && pat != 0u)) key[c] = (ib - 1) * p.npat1 + (int)pat - 1;
+            }
+        }
+        // one pass per histogram: values of the 8 cells, run merge (a run's sum travels to its last cell),
+        // flush of the surviving entries (hist_flush is a warp collective)
+        auto pass = [&](double *h, auto value_of) {
+            int kk[8];
+            double val[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { kk[c] = key[c]; val[c] = (key[c] >= 0) ? value_of(c) : 0.0; }
+#pragma unroll
+            for (int c = 1; c < 8; ++c)
+                if (kk[c] == kk[c - 1] && kk[c] >= 0) {
+                    val[c] += val[c - 1];
+                    kk[c - 1] = -1;
+                }
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (__any_sync(kFull, kk[c] >= 0)) hist_flush(h, kk[c], val[c], lane);
+        };
+        pass(hist, [&](int c) { return mocadd[c] ? 0.0 - (double)pr[c] : 0.0; });
+        if (ISO) {   // cdfmocsig.f90:427-428: gdep(jk)*itmask*zarea and itmask*zarea, REAL(4) chains
+            const float gk = p.gdep[k];
+            pass(hist + hsize, [&](int c) {
+                const float itm = (scrub(ss[c], p.sps) == p.sps) ? 0.0f : 1.0f;
+                return (double)__fmul_rn(__fmul_rn(gk, itm), ar[c]);
+            });
+            pass(hist + 2 * hsize, [&](int c) {
+                const float itm = (scrub(ss[c], p.sps) == p.sps) ? 0.0f : 1.0f;
+                return (double)__fmul_rn(itm, ar[c]);
+            });
+        }
+    }
+}
+
+
+// ---- group-granular compaction (the production path) ---------------------------------------------------------
+// A lane's 8 consecutive cells form a GROUP.  The sweep over a window reads only the pattern bytes, V and the area,
+// forms the fp32 transports and queues the groups that hold at least one contributing cell in a warp-private ring
+// (descriptor + the 8 transports).  As soon as 32 groups are queued the warp runs one DENSE iteration: every lane
+// pops one group, loads its T and S, evaluates the 8 bins in registers, merges equal (bin,pattern) neighbours and
+// flushes to the warp's private histogram.  T/S of windows without contributing cells are never read, the EOS runs
+// on full warps whatever the land/ocean geometry, and nothing per cell goes through shared memory.
+// The loop is software-pipelined: the loads of the next window and the T/S loads of the popped groups are issued
+// together, before either is consumed.  Windows holding a NaN/Inf transport (poison semantics) take
+// sig_window_general() instead.
+#ifndef CDF_SIG_EOS_BATCH
+#define CDF_SIG_EOS_BATCH 4
+#endif
+constexpr int kSigEosBatch = CDF_SIG_EOS_BATCH;   // cells evaluated together (coefficient-major)
+#ifdef CDF_SIG_PIPE
+constexpr int kSigRing = 128;   // >= 32 popped (still read by the dense step) + 31 left over + 32 pushed meanwhile
+#else
+constexpr int kSigRing = 64;    // >= 31 left over + 32 pushed
+#endif
+#ifndef CDF_SIG_PF_SWEEP
+#define CDF_SIG_PF_SWEEP 0      // L2 prefetch of V / area this many of the warp's windows ahead (0 = off)
+#endif
+#ifndef CDF_SIG_PF_TS
+#define CDF_SIG_PF_TS 1         // L2 prefetch of a group's T / S when it is queued
+#endif
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+struct SigQueue {
+    uint4 desc[kSigRing];   // x: float4-vector index of the group's first vector, y: need | two<<8 | k<<16, z/w: pattern words
+    float4 pa[kSigRing];    // transports of cells 0..3
+    float4 pb[kSigRing];    // transports of cells 4..7
+};
+union SigScratch {
+    SigStage st;
+    SigQueue q;
+};
+
+#define FM(a, b, c) fma((a), (b), (c))
+// Fast bins of four cells at once, coefficient-major: sm_100 has no constant-bank operands on DFMA, every coefficient
+// costs a load instruction, so each one is fetched once and applied to the four cells.  Per cell the operations and
+// their order are those of eos_dlr0_fma / eos_dlr123_fma.  Returns the mask of cells whose bin is provably the
+// reference's (see sigma_bin_fast).
+template <bool SIGMA0, int NB>
+__device__ __forceinline__ unsigned sigma_bins_try(const float *tem, const float *sal, const SigParams &p, int *ib)
+{
+    double t[NB], s[NB], acc[NB], q[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+        t[c] = (double)tem[c] * (1.0 / 40.0);
+        const double x = fabs((double)sal[c] + c_eos.rdeltaS) * c_eos.r1_S0;
+        float y0;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"((float)x));
+        double y = (double)y0;
+        y = y * FM(-0.5 * x, y * y, 1.5);           // 2^-22 -> ~2^-43
+        const double sx = x * y;
+        s[c] = FM(FM(-sx, sx, x), 0.5 * y, sx);     // one correction step on the root itself: rounding level
+    }
+#define ALL4(expr) _Pragma("unroll") for (int c = 0; c < NB; ++c) { expr; }
+    ALL4(q[c] = FM(CE(1, 5, 0), s[c], CE(0, 5, 0)))
+    ALL4(acc[c] = FM(CE(0, 6, 0), t[c], q[c]))
+    ALL4(q[c] = FM(CE(2, 4, 0), s[c], CE(1, 4, 0)))
+    ALL4(q[c] = FM(q[c], s[c], CE(0, 4, 0)))
+    ALL4(acc[c] = FM(acc[c], t[c], q[c]))
+    ALL4(q[c] = FM(CE(3, 3, 0), s[c], CE(2, 3, 0)))
+    ALL4(q[c] = FM(q[c], s[c], CE(1, 3, 0)))
+    ALL4(q[c] = FM(q[c], s[c], CE(0, 3, 0)))
+    ALL4(acc[c] = FM(acc[c], t[c], q[c]))
+    ALL4(q[c] = FM(CE(4, 2, 0), s[c], CE(3, 2, 0)))
+    ALL4(q[c] = FM(q[c], s[c], CE(2, 2, 0)))
+    ALL4(q[c] = FM(q[c], s[c], CE(1, 2, 0)))
+    ALL4(q[c] = FM(q[c], s[c], CE(0, 2, 0)))
+    ALL4(acc[c] = FM(acc[c], t[c], q[c]))
+    ALL4(q[c] = FM(CE(5, 1, 0), s[c], CE(4, 1, 0)))
+    ALL4(q[c] = FM(q[c], s[c], CE(3, 1, 0)))
+    ALL4(q[c] = FM(q[c], s[c], CE(2, 1, 0)))
+    ALL4(q[c] = FM(q[c], s[c], CE(1, 1, 0)))
+    ALL4(q[c] = FM(q[c], s[c], CE(0, 1, 0)))
+    ALL4(acc[c] = FM(acc[c], t[c], q[c]))
+    ALL4(q[c] = FM(CE(6, 0, 0), s[c], CE(5, 0, 0)))
+    ALL4(q[c] = FM(q[c], s[c], CE(4, 0, 0)))
+    ALL4(q[c] = FM(q[c], s[c], CE(3, 0, 0)))
+    ALL4(q[c] = FM(q[c], s[c], CE(2, 0, 0)))
+    ALL4(q[c] = FM(q[c], s[c], CE(1, 0, 0)))
+    ALL4(q[c] = FM(q[c], s[c], CE(0, 0, 0)))
+    ALL4(acc[c] = FM(acc[c], t[c], q[c]))
+    if (!SIGMA0) {   // + ((dlr3*h + dlr2)*h + dlr1)*h
+        double r1[NB];
+        const double h = p.dlh;
+        ALL4(q[c] = FM(CE(1, 3, 1), s[c], CE(0, 3, 1)))
+        ALL4(r1[c] = FM(CE(0, 4, 1), t[c], q[c]))
+        ALL4(q[c] = FM(CE(2, 2, 1), s[c], CE(1, 2, 1)))
+        ALL4(q[c] = FM(q[c], s[c], CE(0, 2, 1)))
+        ALL4(r1[c] = FM(r1[c], t[c], q[c]))
+        ALL4(q[c] = FM(CE(3, 1, 1), s[c], CE(2, 1, 1)))
+        ALL4(q[c] = FM(q[c], s[c], CE(1, 1, 1)))
+        ALL4(q[c] = FM(q[c], s[c], CE(0, 1, 1)))
+        ALL4(r1[c] = FM(r1[c], t[c], q[c]))
+        ALL4(q[c] = FM(CE(4, 0, 1), s[c], CE(3, 0, 1)))
+        ALL4(q[c] = FM(q[c], s[c], CE(2, 0, 1)))
+        ALL4(q[c] = FM(q[c], s[c], CE(1, 0, 1)))
+        ALL4(q[c] = FM(q[c], s[c], CE(0, 0, 1)))
+        ALL4(r1[c] = FM(r1[c], t[c], q[c]))
+        double r2[NB];
+        ALL4(q[c] = FM(CE(1, 1, 2), s[c], CE(0, 1, 2)))
+        ALL4(r2[c] = FM(CE(0, 2, 2), t[c], q[c]))
+        ALL4(q[c] = FM(CE(2, 0, 2), s[c], CE(1, 0, 2)))
+        ALL4(q[c] = FM(q[c], s[c], CE(0, 0, 2)))
+        ALL4(r2[c] = FM(r2[c], t[c], q[c]))
+        ALL4(q[c] = FM(CE(1, 0, 3), s[c], CE(0, 0, 3)))
+        ALL4(q[c] = FM(CE(0, 1, 3), t[c], q[c]))
+        ALL4(acc[c] += FM(FM(q[c], h, r2[c]), h, r1[c]) * h)
+    }
+#undef ALL4
+    unsigned ok = 0u;
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+        const double qa = FM(acc[c], p.inv_sigstp, p.qoffset);   // (sigma - sigmin) / sigstp
+        const int i = __double2int_rz(qa);
+        const double fr = qa - (double)i;
+        ib[c] = i;
+        // strictly inside the bin range, farther than the margin from a bin edge, salinity not a mask value
+        if ((unsigned)(i - 1) < (unsigned)(p.nbins - 1) && fabs(fr - 0.5) < p.half_m_margin && sal[c] != 0.0f && sal[c] != p.sps)
+            ok |= 1u << c;
+    }
+    return ok;
+}
+#undef FM
+
+// The reference chain, out of line (rare: cells near a bin edge, clamped cells, land values).
+template <int EOS, bool SIGMA0>
+__device__ __noinline__ int sigma_bin_slow(float tem, float sal, float sigmin, float sigstp, float sps, int nbins, double dlh,
+                                           double dlref)
+{
+    const double dens = (EOS == CDFGPU_EOS_NEUTRAL) ? eos_sigma_neutral(tem, sal) : eos_sigma_exact<SIGMA0>(tem, sal, dlh, dlref);
+    const double itm = (sal == sps) ? 0.0 : 1.0;
+    const float z = __double2float_rn(__dmul_rn(dens, itm));
+    const float q = __fdiv_rn(__fsub_rn(z, sigmin), sigstp);
+    int ib = (q >= 2147483648.0f || q < -2147483648.0f || q != q) ? (int)0x80000000 : __float2int_rz(q);
+    return min(max(ib, 1), nbins);
+}
+
+// hist_flush with a shortcut for a single live lane (a bin boundary inside one lane's group)
+__device__ __forceinline__ void hist_flush_few(double *hist, int key, double val, int lane)
+{
+    const bool live = key >= 0;
+    const unsigned act = __ballot_sync(kFull, live);
+    if ((act & (act - 1u)) == 0u) {   // zero or one live lane
+        if (live) hist[key] += val;
+        __syncwarp();
+        return;
+    }
+    hist_flush(hist, key, val, lane);
+}
+
+// Loads of one sweep step (this lane's group in window (k, win) of row j), issued but not consumed.
+struct SigSweepLoads {
+    float4 va, vb, aa, ab, ea, eb;
+    uint32_t pw0, pw1;
+    uint32_t voff;     // float4-vector index of the group's first vector
+    bool two, any;     // second vector inside the row; something other than excluded cells
+};
+
+__device__ __forceinline__ void sig_sweep_load(const SigParams &p, const uint32_t *__restrict__ patrow, int j, int k, int win,
+                                               int lane, uint64_t pol, SigSweepLoads &L)
+{
+    const uint32_t r = (uint32_t)k * (uint32_t)p.ny + (uint32_t)j;
+    const uint64_t e0 = (uint64_t)r * (uint32_t)p.nx;
+    const uint32_t s = (uint32_t)e0 & 3u;
+    const int nvec = (int)((s + (uint32_t)p.nx + 3u) >> 2);
+    const int v0 = win * kSigWinVec + 2 * lane;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    L.pw0 = 0xffffffffu; L.pw1 = 0xffffffffu;
+    L.va = z4; L.vb = z4; L.aa = z4; L.ab = z4; L.ea = z4; L.eb = z4;
+    L.voff = (uint32_t)(e0 >> 2) + (uint32_t)v0;
+    L.two = v0 + 1 < nvec;
+    L.any = false;
+    if (v0 < nvec) {
+        const uint32_t *pwp = patrow + (size_t)s * p.patplane + v0;
+        L.pw0 = __ldg(pwp);
+        if (L.two) L.pw1 = __ldg(pwp + 1);
+        L.any = (L.pw0 & L.pw1) != 0xffffffffu;
+        if (L.any) {
+            const float4 *pv = reinterpret_cast<const float4 *>(p.zv) + L.voff;
+            const float4 *pa = reinterpret_cast<const float4 *>(p.area) + L.voff;
+            L.va = ld_stream_f4(pv, pol);
+            L.aa = ld_stream_f4(pa, pol);
+            if (L.two) { L.vb = ld_stream_f4(pv + 1, pol); L.ab = ld_stream_f4(pa + 1, pol); }
+            if (p.zveiv) {
+                const float4 *pe = reinterpret_cast<const float4 *>(p.zveiv) + L.voff;
+                L.ea = ld_stream_f4(pe, pol);
+                if (L.two) L.eb = ld_stream_f4(pe + 1, pol);
+            }
+        }
+    }
+}
+
+// Transports and contribution mask of the loaded group; queues it.  Returns false when the window must take the
+// general path (a non-finite transport somewhere in the warp); nothing is queued then.
+template <bool ISO>
+__device__ __forceinline__ bool sig_sweep_push(const SigParams &p, SigQueue &q, const SigSweepLoads &L, int k, int lane, int &qtail)
+{
+    unsigned need = 0u;
+    float pr[8];
+    float zacc = 0.0f;
+    pr[0] = sig_transport(p, L.va.x, L.ea.x, L.aa.x); pr[1] = sig_transport(p, L.va.y, L.ea.y, L.aa.y);
+    pr[2] = sig_transport(p, L.va.z, L.ea.z, L.aa.z); pr[3] = sig_transport(p, L.va.w, L.ea.w, L.aa.w);
+    pr[4] = sig_transport(p, L.vb.x, L.eb.x, L.ab.x); pr[5] = sig_transport(p, L.vb.y, L.eb.y, L.ab.y);
+    pr[6] = sig_transport(p, L.vb.z, L.eb.z, L.ab.z); pr[7] = sig_transport(p, L.vb.w, L.eb.w, L.ab.w);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint32_t pat = __byte_perm(c < 4 ? L.pw0 : L.pw1, 0u, 0x4440u + (c & 3));
+        const bool covered = (pat - 1u) < 254u;            // in some basin and not an excluded column
+        zacc = __fmaf_rn(pr[c], 0.0f, zacc);               // NaN iff some transport of the group is NaN / Inf
+        if (ISO ? covered : (covered && pr[c] != 0.0f)) need |= 1u << c;
+    }
+    if (__any_sync(kFull, zacc != zacc)) return false;
+    const bool has = need != 0u;
+    const unsigned b = __ballot_sync(kFull, has);
+    if (has) {
+        const int pos = (qtail + __popc(b & ((1u << lane) - 1u))) & (kSigRing - 1);
+        q.desc[pos] = make_uint4(L.voff, need | (L.two ? 0x100u : 0u) | ((uint32_t)k << 16), L.pw0, L.pw1);
+        q.pa[pos] = make_float4(pr[0], pr[1], pr[2], pr[3]);
+        q.pb[pos] = make_float4(pr[4], pr[5], pr[6], pr[7]);
+#if CDF_SIG_PF_TS
+        prefetch_l2(reinterpret_cast<const float4 *>(p.zt) + L.voff + 1);
+        prefetch_l2(reinterpret_cast<const float4 *>(p.zs) + L.voff + 1);
+#endif
+    }
+    qtail += __popc(b);
+    return true;
+}
+
+// A popped group: descriptor, transports, and its T / S (/ area) loads in flight.
+template <bool ISO>
+struct SigDense {
+    uint4 d;
+    float4 ta, tb, sa, sb, aa, ab;
+    int slot;        // ring slot (the transports are read from it after the EOS)
+    bool active;
+};
+
+template <bool ISO>
+__device__ __forceinline__ void sig_dense_pop(const SigParams &p, const SigQueue &q, int qhead, int n, int lane, uint64_t pol,
+                                              SigDense<ISO> &D)
+{
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    D.active = lane < n;
+    D.d = make_uint4(0u, 0u, 0u, 0u);
+    D.slot = 0;
+    D.ta = z4; D.tb = z4; D.sa = z4; D.sb = z4; D.aa = z4; D.ab = z4;
+    if (D.active) {
+        const int e = (qhead + lane) & (kSigRing - 1);
+        D.slot = e;
+        D.d = q.desc[e];
+        const bool two = (D.d.y & 0x100u) != 0u;
+        const float4 *pt = reinterpret_cast<const float4 *>(p.zt) + D.d.x;
+        const float4 *ps = reinterpret_cast<const float4 *>(p.zs) + D.d.x;
+        D.ta = ld_stream_f4(pt, pol);
+        D.sa = ld_stream_f4(ps, pol);
+        if (two) { D.tb = ld_stream_f4(pt + 1, pol); D.sb = ld_stream_f4(ps + 1, pol); }
+        if (ISO) {
+            const float4 *pa = reinterpret_cast<const float4 *>(p.area) + D.d.x;
+            D.aa = ld_stream_f4(pa, pol);
+            if (two) D.ab = ld_stream_f4(pa + 1, pol);
+        }
+    }
+}
+
+// EOS, bins, keys, in-lane run merge and flush of a popped group (warp collective).
+template <int EOS, bool SIGMA0, bool ISO>
+__device__ __forceinline__ void sig_dense_compute(const SigParams &p, const SigQueue &q, const SigDense<ISO> &D, double *hist,
+                                                  int hsize, int lane)
+{
+    int key[8];
+    float pr[8], ss[ISO ? 8 : 1], ar[ISO ? 8 : 1];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { key[c] = -1; pr[c] = 0.0f; }
+    if (D.active) {
+        const unsigned need = D.d.y & 255u;
+        float tt[8], sv[8];
+        tt[0] = D.ta.x; tt[1] = D.ta.y; tt[2] = D.ta.z; tt[3] = D.ta.w; tt[4] = D.tb.x; tt[5] = D.tb.y; tt[6] = D.tb.z; tt[7] = D.tb.w;
+        sv[0] = D.sa.x; sv[1] = D.sa.y; sv[2] = D.sa.z; sv[3] = D.sa.w; sv[4] = D.sb.x; sv[5] = D.sb.y; sv[6] = D.sb.z; sv[7] = D.sb.w;
+        if (ISO) {
+            ar[0] = D.aa.x; ar[1] = D.aa.y; ar[2] = D.aa.z; ar[3] = D.aa.w; ar[4] = D.ab.x; ar[5] = D.ab.y; ar[6] = D.ab.z; ar[7] = D.ab.w;
+        }
+        if (p.scrub_ts) {   // missing values other than zero (a zero missing value needs no scrub: x == 0 -> 0)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { tt[c] = scrub(tt[c], p.spt); sv[c] = scrub(sv[c], p.sps); }
+        }
+        if (ISO) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) ss[c] = sv[c];
+        }
+        int ib[8];
+        unsigned bad = 0xffu;
+        if (EOS != CDFGPU_EOS_NEUTRAL && p.qmargin >= 0.0) {
+            unsigned ok = 0u;
+#pragma unroll
+            for (int c0 = 0; c0 < 8; c0 += kSigEosBatch)
+                ok |= sigma_bins_try<SIGMA0, kSigEosBatch>(tt + c0, sv + c0, p, ib + c0) << c0;
+            bad = ~ok & 0xffu;
+        }
+        bad &= need;
+        if (bad) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (bad & (1u << c))
+                    ib[c] = sigma_bin_slow<EOS, SIGMA0>(tt[c], sv[c], p.sigmin, p.sigstp, p.sps, p.nbins, p.dlh, p.dlref);
+        }
+        {
+            const float4 qa = q.pa[D.slot], qb = q.pb[D.slot];
+            pr[0] = qa.x; pr[1] = qa.y; pr[2] = qa.z; pr[3] = qa.w; pr[4] = qb.x; pr[5] = qb.y; pr[6] = qb.z; pr[7] = qb.w;
+        }
+        // keys; a cell that does not contribute is transparent (inherits its left neighbour's key, adds zero), so that a
+        // lane's last run always ends in cell 7
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int pat = (int)__byte_perm(c < 4 ? D.d.z : D.d.w, 0u, 0x4440u + (c & 3));
+            if (need & (1u << c)) key[c] = ib[c] * p.npat1 + (pat - 1 - p.npat1);
+            else {
+                key[c] = (c > 0) ? key[c > 0 ? c - 1 : 0] : -1;
+                pr[c] = 0.0f;
+                if (ISO) ar[c] = 0.0f;
+            }
+        }
+    }
+    auto pass = [&](double *h, auto value_of) {
+        int kk[8];
+        double val[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { kk[c] = key[c]; val[c] = value_of(c); }
+#pragma unroll
+        for (int c = 1; c < 8; ++c)
+            if (kk[c] == kk[c - 1]) {
+                val[c] += val[c - 1];
+                kk[c - 1] = -1;
+            }
+        hist_flush(h, kk[7], val[7], lane);
+        bool extra = false;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) extra |= kk[c] >= 0;
+        if (__any_sync(kFull, extra)) {
+#pragma unroll
+            for (int c = 0; c < 7; ++c)
+                if (__any_sync(kFull, kk[c] >= 0)) hist_flush_few(h, kk[c], val[c], lane);
+        }
+    };
+    pass(hist, [&](int c) { return 0.0 - (double)pr[c]; });
+    if (ISO) {   // cdfmocsig.f90:427-428: gdep(jk)*itmask*zarea and itmask*zarea, REAL(4) chains
+        const float gk = p.gdep[D.d.y >> 16];
+        pass(hist + hsize, [&](int c) {
+            const float itm = (ss[c] == p.sps) ? 0.0f : 1.0f;
+            return (double)__fmul_rn(__fmul_rn(gk, itm), ar[c]);
+        });
+        pass(hist + 2 * hsize, [&](int c) {
+            const float itm = (ss[c] == p.sps) ? 0.0f : 1.0f;
+            return (double)__fmul_rn(itm, ar[c]);
+        });
+    }
+}
+
+// sig_window_general out of line, for the rare windows that hold a NaN / Inf transport
+template <int EOS, bool SIGMA0, bool ISO>
+__device__ __noinline__ void sig_window_general_call(const SigParams &p, SigStage &st, double *hist, unsigned *s_poison, int hsize,
+                                                     int j, int k, int win, int lane)
+{
+    sig_window_general<EOS, SIGMA0, ISO>(p, st, hist, s_poison, hsize, j, k, win, lane, make_evict_first_policy());
+}
+
+// All windows of latitude row j that belong to this warp (w = warp, warp + nwarps, ...; window id = win*(nz-1) + k).
+// One loop with a single pop / compute site: while windows remain, a dense iteration runs whenever 32 groups are
+// queued; afterwards the same loop drains the ring.  Windows with a non-finite transport are only flagged here and
+// handled by a second pass over the warp's windows (the order of the additions into the private histogram does not
+// matter for determinism: it is fixed by the data).
+template <int EOS, bool SIGMA0, bool ISO>
+__device__ __forceinline__ void sig_row_queue(const SigParams &p, SigScratch &scr, double *hist, unsigned *s_poison, int hsize,
+                                              int j, int warp, int nwarps, int total, int lane, uint64_t pol)
+{
+    const int nzm1 = p.nz - 1;
+    const uint32_t *patrow = p.patw + (size_t)j * p.pitchw;
+    int qhead = 0, qtail = 0;   // warp-uniform ring positions
+    int win = 0, k = warp;
+    bool any_weird = false;
+    while (k >= nzm1) { k -= nzm1; ++win; }
+    for (int w = warp;; w += nwarps) {
+        const bool have = w < total;
+        const int count = qtail - qhead;
+        if (!have && count == 0) break;
+        SigSweepLoads L;
+        SigDense<ISO> D;
+        if (have) sig_sweep_load(p, patrow, j, k, win, lane, pol, L);        // (1) this window's V / area loads
+#if CDF_SIG_PF_SWEEP
+        if (w + CDF_SIG_PF_SWEEP * nwarps < total) {   // pull a later window of this warp from HBM into L2
+            int kp = k + CDF_SIG_PF_SWEEP * nwarps, wp = win;
+            while (kp >= nzm1) { kp -= nzm1; ++wp; }
+            const uint64_t e0 = (uint64_t)((uint32_t)kp * (uint32_t)p.ny + (uint32_t)j) * (uint32_t)p.nx;
+            const uint32_t vo = (uint32_t)(e0 >> 2) + (uint32_t)(wp * kSigWinVec + 2 * lane);
+            prefetch_l2(reinterpret_cast<const float4 *>(p.zv) + vo);
+            prefetch_l2(reinterpret_cast<const float4 *>(p.area) + vo);
+        }
+#endif
+#ifndef CDF_SIG_PIPE   // default: push first, then pop what is there (CDF_SIG_PIPE: issue both load sets together)
+        if (have) {
+            if (!sig_sweep_push<ISO>(p, scr.q, L, k, lane, qtail)) any_weird = true;
+            k += nwarps;
+            while (k >= nzm1) { k -= nzm1; ++win; }
+        }
+        __syncwarp();
+        const int cnt2 = qtail - qhead;
+        const int n2 = have ? (cnt2 >= 32 ? 32 : 0) : min(32, cnt2);
+        if (n2) {
+            sig_dense_pop<ISO>(p, scr.q, qhead, n2, lane, pol, D);
+            qhead += n2;
+            sig_dense_compute<EOS, SIGMA0, ISO>(p, scr.q, D, hist, hsize, lane);
+        }
+        continue;
+#endif
+        const int n = have ? (count >= 32 ? 32 : 0) : min(32, count);
+        if (n) {                                                              // (2) T / S loads of the queued groups
+            sig_dense_pop<ISO>(p, scr.q, qhead, n, lane, pol, D);
+            qhead += n;
+        }
+        if (have) {                                                           // (3) consumes (1)
+            if (!sig_sweep_push<ISO>(p, scr.q, L, k, lane, qtail)) any_weird = true;
+            k += nwarps;
+            while (k >= nzm1) { k -= nzm1; ++win; }
+        }
+        __syncwarp();
+        if (n) sig_dense_compute<EOS, SIGMA0, ISO>(p, scr.q, D, hist, hsize, lane);   // (4) consumes (2)
+    }
+    if (any_weird) {   // rare: NaN / Inf transports (poison semantics) -- redo exactly those windows with the general code
+        __syncwarp();
+        win = 0; k = warp;
+        while (k >= nzm1) { k -= nzm1; ++win; }
+        for (int w = warp; w < total; w += nwarps) {
+            SigSweepLoads L;
+            int dummy = 0;
+            sig_sweep_load(p, patrow, j, k, win, lane, pol, L);
+            if (!sig_sweep_push<ISO>(p, scr.q, L, k, lane, dummy)) {
+                __syncwarp();
+                sig_window_general_call<EOS, SIGMA0, ISO>(p, scr.st, hist, s_poison, hsize, j, k, win, lane);
+            }
+            __syncwarp();
+            k += nwarps;
+            while (k >= nzm1) { k -= nzm1; ++win; }
+        }
+    }
+}
+
+template <int EOS, bool SIGMA0, bool ISO, bool QUEUE>
+__global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(const __grid_constant__ SigParams p)
 {
     extern __shared__ double s_mem[];
     const int nwarps = blockDim.x >> 5, nthreads = blockDim.x;     // chosen by the host so that shared memory fits
@@ -280,7 +872,7 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
     constexpr int NH = ISO ? 3 : 1;                                  // histograms per warp: transport [, depth*area, area]
     double *hist_all = s_mem;                                       // [nwarps][NH][nbins][npat1]
     double *comb = hist_all + (size_t)nwarps * NH * hsize;        // [nbins][nb]
-    SigStage *stage_all = reinterpret_cast<SigStage *>(comb + (((size_t)p.nbins * p.nb + 1) & ~(size_t)1));  // 16-B aligned
+    SigScratch *stage_all = reinterpret_cast<SigScratch *>(comb + (((size_t)p.nbins * p.nb + 1) & ~(size_t)1));  // 16-B aligned
     unsigned *s_poison = reinterpret_cast<unsigned *>(stage_all + nwarps);  // [nbins]
     __shared__ int s_ticket[2];
 
@@ -288,7 +880,7 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
     const int nzm1 = p.nz - 1;
     const uint64_t pol = make_evict_first_policy();
     double *hist = hist_all + (size_t)warp * NH * hsize;
-    SigStage &st = stage_all[warp];
+    SigStage &st = stage_all[warp].st;
     const int NV = (p.nx + 6) >> 2;                 // vectors per row, upper bound over the 4 alignments
     const int wpr = (NV + kSigWinVec - 1) / kSigWinVec;  // windows per (level) row
     const int total = nzm1 * wpr;                   // windows of one latitude row j
@@ -314,141 +906,14 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
             // (with the sector-fastest order and nwarps a multiple of the sectors per row, a warp kept ONE sector).
             int win = 0, k = warp;
             while (k >= nzm1) { k -= nzm1; ++win; }
-            for (int w = warp; w < total; w += nwarps) {   // warp-uniform loop: one window of 64 vectors per trip
-                const size_t e0 = ((size_t)k * p.ny + j) * (size_t)p.nx;
-                const int s = (int)(e0 & 3);
-                const int nvec = (s + p.nx + 3) >> 2;
-                const int v0 = win * kSigWinVec + 2 * lane;   // this lane's two consecutive vectors = 8 cells
-                uint32_t pw0 = 0xffffffffu, pw1 = 0xffffffffu;
-                unsigned need = 0u;                            // bit c: cell c needs a bin (contributes)
-                float tt[8], ss[8], pr[8], ar[ISO ? 8 : 1];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) pr[c] = 0.0f;
-                // ---- phase A: load, transport, which cells contribute -----------------------------------------
-                if (v0 < nvec) {
-                    const size_t off = (e0 - s) + 4 * (size_t)v0;
-                    const uint32_t *pwp = p.patw + ((size_t)s * p.ny + j) * p.pitchw + v0;
-                    const bool two = v0 + 1 < nvec;
-                    pw0 = __ldg(pwp);
-                    if (two) pw1 = __ldg(pwp + 1);
-                    if ((pw0 & pw1) != 0xffffffffu) {
-                        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float4 *pv = reinterpret_cast<const float4 *>(p.zv + off);
-                        const float4 *pa = reinterpret_cast<const float4 *>(p.area + off);
-                        const float4 *pt = reinterpret_cast<const float4 *>(p.zt + off);
-                        const float4 *ps = reinterpret_cast<const float4 *>(p.zs + off);
-                        const float4 va = ld_stream_f4(pv, pol), vb = two ? ld_stream_f4(pv + 1, pol) : z4;
-                        const float4 aa = ld_stream_f4(pa, pol), ab = two ? ld_stream_f4(pa + 1, pol) : z4;
-                        const float4 ta = ld_stream_f4(pt, pol), tb = two ? ld_stream_f4(pt + 1, pol) : z4;
-                        const float4 sa = ld_stream_f4(ps, pol), sb = two ? ld_stream_f4(ps + 1, pol) : z4;
-                        float4 ea = z4, eb = z4;
-                        if (p.zveiv) {
-                            const float4 *pe = reinterpret_cast<const float4 *>(p.zveiv + off);
-                            ea = ld_stream_f4(pe, pol);
-                            if (two) eb = ld_stream_f4(pe + 1, pol);
-                        }
-                        pr[0] = sig_transport(p, va.x, ea.x, aa.x); pr[1] = sig_transport(p, va.y, ea.y, aa.y);
-                        pr[2] = sig_transport(p, va.z, ea.z, aa.z); pr[3] = sig_transport(p, va.w, ea.w, aa.w);
-                        pr[4] = sig_transport(p, vb.x, eb.x, ab.x); pr[5] = sig_transport(p, vb.y, eb.y, ab.y);
-                        pr[6] = sig_transport(p, vb.z, eb.z, ab.z); pr[7] = sig_transport(p, vb.w, eb.w, ab.w);
-                        tt[0] = ta.x; tt[1] = ta.y; tt[2] = ta.z; tt[3] = ta.w; tt[4] = tb.x; tt[5] = tb.y; tt[6] = tb.z; tt[7] = tb.w;
-                        ss[0] = sa.x; ss[1] = sa.y; ss[2] = sa.z; ss[3] = sa.w; ss[4] = sb.x; ss[5] = sb.y; ss[6] = sb.z; ss[7] = sb.w;
-                        if (ISO) { ar[0] = aa.x; ar[1] = aa.y; ar[2] = aa.z; ar[3] = aa.w; ar[4] = ab.x; ar[5] = ab.y; ar[6] = ab.z; ar[7] = ab.w; }
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const uint32_t pat = ((c < 4 ? pw0 : pw1) >> (8 * (c & 3))) & 255u;
-                            const bool finite = (__float_as_uint(pr[c]) & 0x7f800000u) != 0x7f800000u;
-                            // excluded cell, exact zero, or finite transport not covered by any basin: contributes nothing.
-                            // With -isodep every covered cell carries area weight into its bin, whatever its transport.
-                            if (ISO ? (pat != 255u && (pat != 0u || (!finite && pr[c] != 0.0f)))
-                                    : (pat != 255u && pr[c] != 0.0f && (pat != 0u || !finite))) need |= 1u << c;
-                        }
-                    }
+            if (QUEUE) {
+                sig_row_queue<EOS, SIGMA0, ISO>(p, stage_all[warp], hist, s_poison, hsize, j, warp, nwarps, total, lane, pol);
+            } else {
+                for (int w = warp; w < total; w += nwarps) {   // warp-uniform loop: one window of 64 vectors per trip
+                    sig_window_general<EOS, SIGMA0, ISO>(p, st, hist, s_poison, hsize, j, k, win, lane, pol);
+                    k += nwarps;
+                    while (k >= nzm1) { k -= nzm1; ++win; }
                 }
-                // ---- compaction: the cells that need the EOS, in (lane, c) order, over the whole warp ------------
-                const int mine = __popc(need);
-                int base = mine;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int o = __shfl_up_sync(kFull, base, d);
-                    if (lane >= d) base += o;
-                }
-                const int nneed = __shfl_sync(kFull, base, 31);
-                base -= mine;
-                if (nneed > 0) {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        if (need & (1u << c)) {
-                            const int e = base + __popc(need & ((1u << c) - 1u));
-                            st.ct[e] = tt[c];
-                            st.cs[e] = ss[c];
-                            st.slot[e] = (uint8_t)(c * 32 + lane);
-                        }
-                    __syncwarp();
-                    // ---- phase B: dense EOS + bin over the compacted list ---------------------------------------
-                    for (int e = lane; e < nneed; e += 32)
-                        st.bin[st.slot[e]] =
-                            (uint16_t)sigma_bin_fast<EOS, SIGMA0>(scrub(st.ct[e], p.spt), scrub(st.cs[e], p.sps), p);
-                    __syncwarp();
-                    // ---- phase C: the lane's 8 consecutive cells, all in registers: key/value per cell, equal
-                    // (bin,pattern) neighbours merged (a run's sum travels to its last cell), then the surviving entries
-                    // are flushed to the warp's private histogram (hist_flush is a warp collective) ----------------
-                    int key[8];
-                    bool mocadd[8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        key[c] = -1;
-                        mocadd[c] = false;
-                        if (need & (1u << c)) {
-                            const uint32_t pat = ((c < 4 ? pw0 : pw1) >> (8 * (c & 3))) & 255u;
-                            const int ib = st.bin[c * 32 + lane];
-                            bool add = true;
-                            if ((__float_as_uint(pr[c]) & 0x7f800000u) == 0x7f800000u) {
-                                // NaN/Inf transport: basin b is poisoned iff (0-p)*mask_b is NaN (NaN*x, or Inf*0)
-                                unsigned bits = 0u;
-                                for (int b = 0; b < p.nb; ++b) {
-                                    const double cc = __dmul_rn(0.0 - (double)pr[c], c_patw[pat][b]);
-                                    if (cc != cc) bits |= 1u << b;
-                                }
-                                if (bits) atomicOr(s_poison + (ib - 1), bits);
-                                add = !(pr[c] != pr[c] || pat == 0u);  // an Inf with a covering basin still accumulates
-                            }
-                            mocadd[c] = add;
-                            if (add || (ISO && pat != 0u)) key[c] = (ib - 1) * p.npat1 + (int)pat - 1;
-                        }
-                    }
-                    // one pass per histogram: values of the 8 cells, run merge (a run's sum travels to its last cell),
-                    // flush of the surviving entries (hist_flush is a warp collective)
-                    auto pass = [&](double *h, auto value_of) {
-                        int kk[8];
-                        double val[8];
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) { kk[c] = key[c]; val[c] = (key[c] >= 0) ? value_of(c) : 0.0; }
-#pragma unroll
-                        for (int c = 1; c < 8; ++c)
-                            if (kk[c] == kk[c - 1] && kk[c] >= 0) {
-                                val[c] += val[c - 1];
-                                kk[c - 1] = -1;
-                            }
-#pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            if (__any_sync(kFull, kk[c] >= 0)) hist_flush(h, kk[c], val[c], lane);
-                    };
-                    pass(hist, [&](int c) { return mocadd[c] ? 0.0 - (double)pr[c] : 0.0; });
-                    if (ISO) {   // cdfmocsig.f90:427-428: gdep(jk)*itmask*zarea and itmask*zarea, REAL(4) chains
-                        const float gk = p.gdep[k];
-                        pass(hist + hsize, [&](int c) {
-                            const float itm = (scrub(ss[c], p.sps) == p.sps) ? 0.0f : 1.0f;
-                            return (double)__fmul_rn(__fmul_rn(gk, itm), ar[c]);
-                        });
-                        pass(hist + 2 * hsize, [&](int c) {
-                            const float itm = (scrub(ss[c], p.sps) == p.sps) ? 0.0f : 1.0f;
-                            return (double)__fmul_rn(itm, ar[c]);
-                        });
-                    }
-                }
-                k += nwarps;
-                while (k >= nzm1) { k -= nzm1; ++win; }
             }
         }
         __syncthreads();

@@ -12,7 +12,10 @@ from pathlib import Path
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-SO_PATH = PKG / "libcdfgpu.so"
+import os
+
+# CDFGPU_LIB: path of an alternative build of the library (A/B experiments with compile-time variants, tools/ab_variants.sh)
+SO_PATH = Path(os.environ["CDFGPU_LIB"]) if os.environ.get("CDFGPU_LIB") else PKG / "libcdfgpu.so"
 
 EOS80, TEOS10, NEUTRAL = 0, 1, 2
 
