@@ -25,7 +25,10 @@
 
 namespace cdfgpu {
 
-constexpr int kSigWarps = 24;
+#ifndef CDF_SIG_WARPS
+#define CDF_SIG_WARPS 16
+#endif
+constexpr int kSigWarps = CDF_SIG_WARPS;
 constexpr int kSigThreads = kSigWarps * 32;
 constexpr int kSigMaxPat = 32;
 constexpr int kSigWinVec = 64;  // one warp step = 64 float4 vectors = 256 cells, 8 consecutive cells per lane
@@ -43,6 +46,7 @@ struct SigParams {
     const float *__restrict__ zveiv;                                   // optional, may be null
     const float *__restrict__ area;                                    // (nz-1, ny, nx) fl32(e1v*e3v)
     const uint32_t *__restrict__ patw;                                 // [4][ny][pitchw] pattern bytes, shifted copies
+    const uint8_t *__restrict__ cov8;                                  // [4][ny][pitchw/2] coverage bits of each 8-cell group
     double *__restrict__ out;                                          // (ny, nbins, nb)
     double *__restrict__ out_iso;                                      // -isodep: (ny, nbins, nb) mean isopycnal depth
     const float *__restrict__ gdep;                                    // -isodep: -gdept(k), (nz)
@@ -59,6 +63,7 @@ struct SigParams {
     double qoffset;                               // (dlref - 1000 - sigmin) / sigstp
     size_t patplane;                              // words per pre-shifted pattern plane = ny * pitchw
     int scrub_ts;                                 // T or S missing value is not zero
+    int scrub_v;                                  // V missing value is not zero
 };
 
 // ---- equation of state ----------------------------------------------------------------------------------------
@@ -422,24 +427,12 @@ __device__ __forceinline__ void sig_window_general(const SigParams &p, SigStage 
 // pops one group, loads its T and S, evaluates the 8 bins in registers, merges equal (bin,pattern) neighbours and
 // flushes to the warp's private histogram.  T/S of windows without contributing cells are never read, the EOS runs
 // on full warps whatever the land/ocean geometry, and nothing per cell goes through shared memory.
-// The loop is software-pipelined: the loads of the next window and the T/S loads of the popped groups are issued
-// together, before either is consumed.  Windows holding a NaN/Inf transport (poison semantics) take
-// sig_window_general() instead.
+// Windows holding a NaN/Inf transport (poison semantics) take sig_window_general() instead.
 #ifndef CDF_SIG_EOS_BATCH
 #define CDF_SIG_EOS_BATCH 4
 #endif
 constexpr int kSigEosBatch = CDF_SIG_EOS_BATCH;   // cells evaluated together (coefficient-major)
-#ifdef CDF_SIG_PIPE
-constexpr int kSigRing = 128;   // >= 32 popped (still read by the dense step) + 31 left over + 32 pushed meanwhile
-#else
-constexpr int kSigRing = 64;    // >= 31 left over + 32 pushed
-#endif
-#ifndef CDF_SIG_PF_SWEEP
-#define CDF_SIG_PF_SWEEP 0      // L2 prefetch of V / area this many of the warp's windows ahead (0 = off)
-#endif
-#ifndef CDF_SIG_PF_TS
-#define CDF_SIG_PF_TS 1         // L2 prefetch of a group's T / S when it is queued
-#endif
+constexpr int kSigRing = 64;                      // >= 31 left over + 32 pushed
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 struct SigQueue {
     uint4 desc[kSigRing];   // x: float4-vector index of the group's first vector, y: need | two<<8 | k<<16, z/w: pattern words
@@ -568,79 +561,65 @@ __device__ __forceinline__ void hist_flush_few(double *hist, int key, double val
     hist_flush(hist, key, val, lane);
 }
 
-// Loads of one sweep step (this lane's group in window (k, win) of row j), issued but not consumed.
-struct SigSweepLoads {
-    float4 va, vb, aa, ab, ea, eb;
-    uint32_t pw0, pw1;
-    uint32_t voff;     // float4-vector index of the group's first vector
-    bool two, any;     // second vector inside the row; something other than excluded cells
-};
-
-__device__ __forceinline__ void sig_sweep_load(const SigParams &p, const uint32_t *__restrict__ patrow, int j, int k, int win,
-                                               int lane, uint64_t pol, SigSweepLoads &L)
+// One sweep step: transports and contribution mask of this lane's group in window (k, win) of row j; queues the group
+// when it contributes.  Reads V, the area and ONE byte of the pre-computed coverage plane (bit c: cell c of the group
+// lies in some basin and is not an excluded column).  Returns false when the window must take the general path (a
+// non-finite transport somewhere in the warp); nothing is queued then.
+template <bool ISO>
+__device__ __forceinline__ bool sig_sweep_window(const SigParams &p, SigQueue &q, int j, int k, int win, int lane, uint64_t pol,
+                                                 int &qtail)
 {
     const uint32_t r = (uint32_t)k * (uint32_t)p.ny + (uint32_t)j;
     const uint64_t e0 = (uint64_t)r * (uint32_t)p.nx;
     const uint32_t s = (uint32_t)e0 & 3u;
     const int nvec = (int)((s + (uint32_t)p.nx + 3u) >> 2);
     const int v0 = win * kSigWinVec + 2 * lane;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    L.pw0 = 0xffffffffu; L.pw1 = 0xffffffffu;
-    L.va = z4; L.vb = z4; L.aa = z4; L.ab = z4; L.ea = z4; L.eb = z4;
-    L.voff = (uint32_t)(e0 >> 2) + (uint32_t)v0;
-    L.two = v0 + 1 < nvec;
-    L.any = false;
-    if (v0 < nvec) {
-        const uint32_t *pwp = patrow + (size_t)s * p.patplane + v0;
-        L.pw0 = __ldg(pwp);
-        if (L.two) L.pw1 = __ldg(pwp + 1);
-        L.any = (L.pw0 & L.pw1) != 0xffffffffu;
-        if (L.any) {
-            const float4 *pv = reinterpret_cast<const float4 *>(p.zv) + L.voff;
-            const float4 *pa = reinterpret_cast<const float4 *>(p.area) + L.voff;
-            L.va = ld_stream_f4(pv, pol);
-            L.aa = ld_stream_f4(pa, pol);
-            if (L.two) { L.vb = ld_stream_f4(pv + 1, pol); L.ab = ld_stream_f4(pa + 1, pol); }
-            if (p.zveiv) {
-                const float4 *pe = reinterpret_cast<const float4 *>(p.zveiv) + L.voff;
-                L.ea = ld_stream_f4(pe, pol);
-                if (L.two) L.eb = ld_stream_f4(pe + 1, pol);
-            }
-        }
-    }
-}
-
-// Transports and contribution mask of the loaded group; queues it.  Returns false when the window must take the
-// general path (a non-finite transport somewhere in the warp); nothing is queued then.
-template <bool ISO>
-__device__ __forceinline__ bool sig_sweep_push(const SigParams &p, SigQueue &q, const SigSweepLoads &L, int k, int lane, int &qtail)
-{
+    const uint32_t voff = (uint32_t)(e0 >> 2) + (uint32_t)v0;
+    const uint32_t pidx = (s * (uint32_t)p.ny + (uint32_t)j) * (uint32_t)p.pitchw + (uint32_t)v0;   // pattern word of the group
+    const bool two = v0 + 1 < nvec;
     unsigned need = 0u;
-    float pr[8];
     float zacc = 0.0f;
-    pr[0] = sig_transport(p, L.va.x, L.ea.x, L.aa.x); pr[1] = sig_transport(p, L.va.y, L.ea.y, L.aa.y);
-    pr[2] = sig_transport(p, L.va.z, L.ea.z, L.aa.z); pr[3] = sig_transport(p, L.va.w, L.ea.w, L.aa.w);
-    pr[4] = sig_transport(p, L.vb.x, L.eb.x, L.ab.x); pr[5] = sig_transport(p, L.vb.y, L.eb.y, L.ab.y);
-    pr[6] = sig_transport(p, L.vb.z, L.eb.z, L.ab.z); pr[7] = sig_transport(p, L.vb.w, L.eb.w, L.ab.w);
+    float pr[8];
+    if (v0 < nvec) {
+        const unsigned cov = p.cov8[pidx >> 1];
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 *pv = reinterpret_cast<const float4 *>(p.zv) + voff;
+        const float4 *pa = reinterpret_cast<const float4 *>(p.area) + voff;
+        float4 va = ld_stream_f4(pv, pol), aa = ld_stream_f4(pa, pol);
+        float4 vb = z4, ab = z4;
+        if (two) { vb = ld_stream_f4(pv + 1, pol); ab = ld_stream_f4(pa + 1, pol); }
+        float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+        const float a[8] = {aa.x, aa.y, aa.z, aa.w, ab.x, ab.y, ab.z, ab.w};
+        if (p.scrub_v) {   // a zero missing value needs no scrub
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const uint32_t pat = __byte_perm(c < 4 ? L.pw0 : L.pw1, 0u, 0x4440u + (c & 3));
-        const bool covered = (pat - 1u) < 254u;            // in some basin and not an excluded column
-        zacc = __fmaf_rn(pr[c], 0.0f, zacc);               // NaN iff some transport of the group is NaN / Inf
-        if (ISO ? covered : (covered && pr[c] != 0.0f)) need |= 1u << c;
+            for (int c = 0; c < 8; ++c) v[c] = scrub(v[c], p.spv);
+        }
+        if (p.zveiv) {     // -eiv: the bolus velocity is read here (rare option; its latency is not hidden)
+            const float4 *pe = reinterpret_cast<const float4 *>(p.zveiv) + voff;
+            const float4 ea = ld_stream_f4(pe, pol), eb = two ? ld_stream_f4(pe + 1, pol) : z4;
+            const float e[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[c] = __fadd_rn(v[c], e[c]);
+        }
+        unsigned nz = 0u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            pr[c] = __fmul_rn(v[c], a[c]);
+            zacc = __fmaf_rn(pr[c], 0.0f, zacc);   // NaN iff some transport of the group is NaN / Inf
+            if (pr[c] != 0.0f) nz |= 1u << c;
+        }
+        need = ISO ? cov : (cov & nz);
     }
     if (__any_sync(kFull, zacc != zacc)) return false;
     const bool has = need != 0u;
     const unsigned b = __ballot_sync(kFull, has);
     if (has) {
         const int pos = (qtail + __popc(b & ((1u << lane) - 1u))) & (kSigRing - 1);
-        q.desc[pos] = make_uint4(L.voff, need | (L.two ? 0x100u : 0u) | ((uint32_t)k << 16), L.pw0, L.pw1);
+        q.desc[pos] = make_uint4(voff, need | (two ? 0x100u : 0u) | ((uint32_t)k << 16), pidx, 0u);
         q.pa[pos] = make_float4(pr[0], pr[1], pr[2], pr[3]);
         q.pb[pos] = make_float4(pr[4], pr[5], pr[6], pr[7]);
-#if CDF_SIG_PF_TS
-        prefetch_l2(reinterpret_cast<const float4 *>(p.zt) + L.voff + 1);
-        prefetch_l2(reinterpret_cast<const float4 *>(p.zs) + L.voff + 1);
-#endif
+        prefetch_l2(reinterpret_cast<const float4 *>(p.zt) + voff + 1);   // the dense step finds T / S in L2
+        prefetch_l2(reinterpret_cast<const float4 *>(p.zs) + voff + 1);
     }
     qtail += __popc(b);
     return true;
@@ -651,7 +630,8 @@ template <bool ISO>
 struct SigDense {
     uint4 d;
     float4 ta, tb, sa, sb, aa, ab;
-    int slot;        // ring slot (the transports are read from it after the EOS)
+    uint32_t pw0, pw1;   // pattern bytes of the 8 cells
+    int slot;            // ring slot (the transports are read from it after the EOS)
     bool active;
 };
 
@@ -663,12 +643,15 @@ __device__ __forceinline__ void sig_dense_pop(const SigParams &p, const SigQueue
     D.active = lane < n;
     D.d = make_uint4(0u, 0u, 0u, 0u);
     D.slot = 0;
+    D.pw0 = 0u; D.pw1 = 0u;
     D.ta = z4; D.tb = z4; D.sa = z4; D.sb = z4; D.aa = z4; D.ab = z4;
     if (D.active) {
         const int e = (qhead + lane) & (kSigRing - 1);
         D.slot = e;
         D.d = q.desc[e];
         const bool two = (D.d.y & 0x100u) != 0u;
+        D.pw0 = __ldg(p.patw + D.d.z);
+        if (two) D.pw1 = __ldg(p.patw + D.d.z + 1);
         const float4 *pt = reinterpret_cast<const float4 *>(p.zt) + D.d.x;
         const float4 *ps = reinterpret_cast<const float4 *>(p.zs) + D.d.x;
         D.ta = ld_stream_f4(pt, pol);
@@ -731,7 +714,7 @@ __device__ __forceinline__ void sig_dense_compute(const SigParams &p, const SigQ
         // lane's last run always ends in cell 7
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const int pat = (int)__byte_perm(c < 4 ? D.d.z : D.d.w, 0u, 0x4440u + (c & 3));
+            const int pat = (int)__byte_perm(c < 4 ? D.pw0 : D.pw1, 0u, 0x4440u + (c & 3));
             if (need & (1u << c)) key[c] = ib[c] * p.npat1 + (pat - 1 - p.npat1);
             else {
                 key[c] = (c > 0) ? key[c > 0 ? c - 1 : 0] : -1;
@@ -793,66 +776,36 @@ __device__ __forceinline__ void sig_row_queue(const SigParams &p, SigScratch &sc
                                               int j, int warp, int nwarps, int total, int lane, uint64_t pol)
 {
     const int nzm1 = p.nz - 1;
-    const uint32_t *patrow = p.patw + (size_t)j * p.pitchw;
     int qhead = 0, qtail = 0;   // warp-uniform ring positions
     int win = 0, k = warp;
     bool any_weird = false;
     while (k >= nzm1) { k -= nzm1; ++win; }
-    for (int w = warp;; w += nwarps) {
-        const bool have = w < total;
-        const int count = qtail - qhead;
-        if (!have && count == 0) break;
-        SigSweepLoads L;
-        SigDense<ISO> D;
-        if (have) sig_sweep_load(p, patrow, j, k, win, lane, pol, L);        // (1) this window's V / area loads
-#if CDF_SIG_PF_SWEEP
-        if (w + CDF_SIG_PF_SWEEP * nwarps < total) {   // pull a later window of this warp from HBM into L2
-            int kp = k + CDF_SIG_PF_SWEEP * nwarps, wp = win;
-            while (kp >= nzm1) { kp -= nzm1; ++wp; }
-            const uint64_t e0 = (uint64_t)((uint32_t)kp * (uint32_t)p.ny + (uint32_t)j) * (uint32_t)p.nx;
-            const uint32_t vo = (uint32_t)(e0 >> 2) + (uint32_t)(wp * kSigWinVec + 2 * lane);
-            prefetch_l2(reinterpret_cast<const float4 *>(p.zv) + vo);
-            prefetch_l2(reinterpret_cast<const float4 *>(p.area) + vo);
-        }
-#endif
-#ifndef CDF_SIG_PIPE   // default: push first, then pop what is there (CDF_SIG_PIPE: issue both load sets together)
-        if (have) {
-            if (!sig_sweep_push<ISO>(p, scr.q, L, k, lane, qtail)) any_weird = true;
+    // One trip: sweep one window and queue its groups, then run a dense iteration if 32 groups are queued; after the
+    // last window the same loop drains the ring (single pop / compute site).
+    for (int w = warp; w < total || qtail != qhead;) {
+        if (w < total) {
+            if (!sig_sweep_window<ISO>(p, scr.q, j, k, win, lane, pol, qtail)) any_weird = true;
+            w += nwarps;
             k += nwarps;
             while (k >= nzm1) { k -= nzm1; ++win; }
+            __syncwarp();
         }
-        __syncwarp();
-        const int cnt2 = qtail - qhead;
-        const int n2 = have ? (cnt2 >= 32 ? 32 : 0) : min(32, cnt2);
-        if (n2) {
-            sig_dense_pop<ISO>(p, scr.q, qhead, n2, lane, pol, D);
-            qhead += n2;
-            sig_dense_compute<EOS, SIGMA0, ISO>(p, scr.q, D, hist, hsize, lane);
-        }
-        continue;
-#endif
-        const int n = have ? (count >= 32 ? 32 : 0) : min(32, count);
-        if (n) {                                                              // (2) T / S loads of the queued groups
+        const int cnt = qtail - qhead;
+        const int n = (w < total) ? (cnt >= 32 ? 32 : 0) : min(32, cnt);
+        if (n) {
+            SigDense<ISO> D;
             sig_dense_pop<ISO>(p, scr.q, qhead, n, lane, pol, D);
             qhead += n;
+            sig_dense_compute<EOS, SIGMA0, ISO>(p, scr.q, D, hist, hsize, lane);
         }
-        if (have) {                                                           // (3) consumes (1)
-            if (!sig_sweep_push<ISO>(p, scr.q, L, k, lane, qtail)) any_weird = true;
-            k += nwarps;
-            while (k >= nzm1) { k -= nzm1; ++win; }
-        }
-        __syncwarp();
-        if (n) sig_dense_compute<EOS, SIGMA0, ISO>(p, scr.q, D, hist, hsize, lane);   // (4) consumes (2)
     }
     if (any_weird) {   // rare: NaN / Inf transports (poison semantics) -- redo exactly those windows with the general code
         __syncwarp();
         win = 0; k = warp;
         while (k >= nzm1) { k -= nzm1; ++win; }
         for (int w = warp; w < total; w += nwarps) {
-            SigSweepLoads L;
             int dummy = 0;
-            sig_sweep_load(p, patrow, j, k, win, lane, pol, L);
-            if (!sig_sweep_push<ISO>(p, scr.q, L, k, lane, dummy)) {
+            if (!sig_sweep_window<ISO>(p, scr.q, j, k, win, lane, pol, dummy)) {
                 __syncwarp();
                 sig_window_general_call<EOS, SIGMA0, ISO>(p, scr.st, hist, s_poison, hsize, j, k, win, lane);
             }
@@ -917,16 +870,19 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
             }
         }
         __syncthreads();
-        // private histograms -> one (fixed order: deterministic), patterns -> basins, /1e6, poison handling
+        // private histograms -> one (fixed order w = 0..nwarps-1: deterministic), in place in warp 0's copy; then
+        // patterns -> basins, /1e6, poison handling
+        for (int t = tid; t < NH * hsize; t += nthreads) {
+            double hq = 0.0;
+            for (int w = 0; w < nwarps; ++w) hq += hist_all[(size_t)w * NH * hsize + t];
+            hist_all[t] = hq;
+        }
+        __syncthreads();
         auto combine = [&](int which, int bin, int b) {
             double h = 0.0;
             for (int q = 1; q < p.npat; ++q) {
                 const double wgt = c_patw[q][b];
-                if (wgt != 0.0) {
-                    double hq = 0.0;
-                    for (int w = 0; w < nwarps; ++w) hq += hist_all[((size_t)w * NH + which) * hsize + bin * p.npat1 + q - 1];
-                    h += hq * wgt;
-                }
+                if (wgt != 0.0) h += hist_all[which * hsize + bin * p.npat1 + q - 1] * wgt;
             }
             return h;
         };

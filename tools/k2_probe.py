@@ -6,13 +6,14 @@ from cdftools_b200 import lib, synth
 import oracle
 grid = sys.argv[1] if len(sys.argv) > 1 else "ORCA025"
 pref = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0
+vscale = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0   # 0: no cell contributes -> times the sweep alone
 m = synth.make_mesh(grid)
 ib = oracle.basin_masks(*synth.basin_mask_inputs(m))
 nb = ib.shape[2]
 lib.init(0, 3)
 g = torch.Generator(device="cuda"); g.manual_seed(1)
 vm = torch.from_numpy(m.vmask[:-1].astype(np.float32)).cuda()
-recs = [(0.1 * torch.randn((m.nz - 1, m.ny, m.nx), device="cuda", generator=g)) * vm for _ in range(2)]
+recs = [(0.1 * vscale * torch.randn((m.nz - 1, m.ny, m.nx), device="cuda", generator=g)) * vm for _ in range(2)]
 tm = torch.from_numpy(m.tmask[:-1].astype(np.float32)).cuda()
 z = torch.from_numpy(m.gdept_1d[:-1].astype(np.float32)).cuda()[:, None, None]
 cl = torch.cos(torch.deg2rad(torch.from_numpy(m.gphiv).cuda()))[None]

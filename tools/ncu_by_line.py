@@ -18,6 +18,8 @@ for ln in open(sys.argv[2]):
     if m: cur = (m.group(1).split('/')[-1], int(m.group(2))); continue
     m = re.match(r'\s+/\*([0-9a-f]{4,})\*/', ln)
     if m: line_of[int(m.group(1), 16)] = cur
+import os
+SORTKEY = 1 if os.environ.get("BY_SAMPLES") else 0
 agg = collections.defaultdict(lambda: [0, 0, 0])
 tot = [0, 0]
 for a, n, s, t in insts:
@@ -26,12 +28,12 @@ for a, n, s, t in insts:
     tot[0] += n; tot[1] += s
 print('total warp-inst %d samples %d' % tuple(tot))
 src = {}
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(sys.argv[3]) if len(sys.argv) > 3 else 40]:
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][SORTKEY])[:int(sys.argv[3]) if len(sys.argv) > 3 else 40]:
     txt = ''
     if k:
         f = k[0]
         if f not in src:
-            try: src[f] = open('cdftools_b200/csrc/' + f).read().split('\n')
+            try: src[f] = open(os.environ.get("SRC_DIR", "cdftools_b200/csrc/") + f).read().split('\n')
             except Exception: src[f] = []
         if 0 < k[1] <= len(src[f]): txt = src[f][k[1] - 1].strip()[:80]
     print('%5.1f%% inst %5.1f%% smp  thr/inst %4.1f  %s:%s  %s' % (100 * v[0] / tot[0], 100 * v[1] / max(tot[1], 1), v[2] / max(v[0], 1), k[0] if k else '?', k[1] if k else '', txt))

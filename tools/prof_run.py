@@ -1,5 +1,5 @@
 """Short kernel-only driver for ncu captures: python tools/prof_run.py {k1|k2} [grid] [pref] [noise]"""
-import sys
+import sys, os
 import numpy as np, torch
 sys.path.insert(0, ".")
 from cdftools_b200 import lib, synth
@@ -13,7 +13,7 @@ ib = oracle.basin_masks(*synth.basin_mask_inputs(m))
 lib.init(0, 3)
 g = torch.Generator(device="cuda"); g.manual_seed(1)
 vm = torch.from_numpy(m.vmask[:-1].astype(np.float32)).cuda()
-recs = [(0.1 * torch.randn((m.nz - 1, m.ny, m.nx), device="cuda", generator=g)) * vm for _ in range(3)]
+recs = [(0.1 * float(os.environ.get("VSCALE", "1")) * torch.randn((m.nz - 1, m.ny, m.nx), device="cuda", generator=g)) * vm for _ in range(3)]
 st = torch.cuda.Stream()
 if which == "k1":
     e3m = oracle.mask_e3v(m.e3v_0, m.vmask.astype(np.float32))
