@@ -459,10 +459,10 @@ __device__ __forceinline__ unsigned sigma_bins_try(const float *tem, const float
         const double x = fabs((double)sal[c] + c_eos.rdeltaS) * c_eos.r1_S0;
         float y0;
         asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"((float)x));
-        double y = (double)y0;
-        y = y * FM(-0.5 * x, y * y, 1.5);           // 2^-22 -> ~2^-43
-        const double sx = x * y;
-        s[c] = FM(FM(-sx, sx, x), 0.5 * y, sx);     // one correction step on the root itself: rounding level
+        const double y = (double)y0;                // 1/sqrt(x) to 2^-22
+        const double sx = x * y;                    // sqrt(x) to 2^-22
+        s[c] = FM(FM(-sx, sx, x), 0.5 * y, sx);     // one Newton step on the root: ~2^-43 relative (|dsigma/ds| < 4e3: far
+                                                    // below the 1e-9 kg/m3 evaluation slop the margin allows for)
     }
 #define ALL4(expr) _Pragma("unroll") for (int c = 0; c < NB; ++c) { expr; }
     ALL4(q[c] = FM(CE(1, 5, 0), s[c], CE(0, 5, 0)))
@@ -897,9 +897,21 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
             }
         }
         __syncthreads();
-        if (tid < p.nb) {  // integrate from the densest bin, sequentially as the reference does (:472-475)
+        if (tid < p.nb) {  // integrate from the densest bin, sequentially as the reference does (:472-475); the loads
+                           // of 8 bins are issued ahead of the dependent chain of additions
             double psi = comb[(p.nbins - 1) * p.nb + tid];
-            for (int bin = p.nbins - 2; bin >= 0; --bin) {
+            int bin = p.nbins - 2;
+            for (; bin >= 7; bin -= 8) {
+                double h[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) h[u] = comb[(bin - u) * p.nb + tid];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    psi = psi + h[u];
+                    comb[(bin - u) * p.nb + tid] = psi;
+                }
+            }
+            for (; bin >= 0; --bin) {
                 psi = psi + comb[bin * p.nb + tid];
                 comb[bin * p.nb + tid] = psi;
             }

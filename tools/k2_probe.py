@@ -1,5 +1,5 @@
 """K2-only timing on device-resident synthetic records: python tools/k2_probe.py [grid] [pref] (prints one JSON line per noise level)."""
-import sys, json
+import sys, json, os
 import numpy as np, torch
 sys.path.insert(0, ".")
 from cdftools_b200 import lib, synth
@@ -18,6 +18,7 @@ tm = torch.from_numpy(m.tmask[:-1].astype(np.float32)).cuda()
 z = torch.from_numpy(m.gdept_1d[:-1].astype(np.float32)).cuda()[:, None, None]
 cl = torch.cos(torch.deg2rad(torch.from_numpy(m.gphiv).cuda()))[None]
 nbins, smin, sstp = {0.0: (104, 23.0, 0.05), 2000.0: (158, 30.0, 0.05), 1000.0: (88, 24.0, 0.1)}[pref]
+nbins = int(os.environ.get('NBINS', nbins))
 lib.cdfmocsig_setup(m.e1v, m.e3v_0, ib, m.nz, nbins, smin, sstp, pref, 0)
 st = torch.cuda.Stream()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
