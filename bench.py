@@ -247,8 +247,8 @@ def run_ours(args):
     for r in range(n_res):
         v = torch.randn(shape3, device="cuda", generator=gen, dtype=torch.float32).mul_(0.1).mul_(vmask)
         if sig:   # same stratified, meridionally varying T/S as synth.make_ts_record, white noise 0.15 K
-            t = (tbase + 0.15 * torch.randn(shape3, device="cuda", generator=gen) + 0.5 * np.sin(0.3 * r)).mul_(tmask)
-            s = (sbase + 0.03 * torch.randn(shape3, device="cuda", generator=gen)).mul_(tmask)
+            t = (tbase + args.ts_noise * torch.randn(shape3, device="cuda", generator=gen) + 0.5 * np.sin(0.3 * r)).mul_(tmask)
+            s = (sbase + 0.2 * args.ts_noise * torch.randn(shape3, device="cuda", generator=gen)).mul_(tmask)
             recs.append((v, t.float().contiguous(), s.float().contiguous()))
         else:
             recs.append((v,))
@@ -317,8 +317,8 @@ def run_ours(args):
                     "peak_source": peak_src, "frac_of_8TBps_spec": achieved / 8000.0,
                     "note": "per-GPU figure; at N>1 the launch time includes the overlapped NCCL slab gather"}
         if sig:
-            roofline["second_bound"] = ("fp64 issue: ~55 fp64 instructions + sqrt per wet cell (FMA-evaluated EOS with "
-                                        "exact fallback); see DESIGN.md")
+            roofline["second_bound"] = ("instruction issue / fp64 pipe: ~60 instructions (47 fp64) per contributing cell for the "
+                                        "FMA-evaluated EOS with exact fallback, plus the histogram flush; see DESIGN.md")
         tp = ROOT / "profiles" / ("k2_traffic.json" if sig else "k1_traffic.json")
         if tp.exists() and spec["grid"] == "ORCA025":
             try:
@@ -410,7 +410,10 @@ def run_ours(args):
                 "parity_check": parity}
         if sig:
             line["config"].update({"pref": spec["pref"], "sigmin": spec["bins"][0], "sigstp": spec["bins"][1],
-                                   "nbins": spec["bins"][2], "eos": "EOS80 polynomial"})
+                                   "nbins": spec["bins"][2], "eos": "EOS80 polynomial",
+                                   "ts_noise_K": args.ts_noise,
+                                   "ts_noise": "white, cell to cell (0.15 K: every neighbour in another density class, the "
+                                               "worst case for run merging; 0: as smooth as the stratification)"})
         if cb:
             line["cpu_baseline"] = cb
         print(json.dumps(line))
@@ -430,6 +433,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
+    ap.add_argument("--ts-noise", type=float, default=0.15,
+                    help="cdfmocsig workloads: amplitude (K) of the cell-to-cell white noise on T (x0.2 on S); 0.15 is the "
+                         "worst case for density-class run merging, 0 gives fields as smooth as the stratification")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
