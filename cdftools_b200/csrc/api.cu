@@ -10,6 +10,7 @@
 #include "moc_kernel_tma.cuh"
 #include "mocsig_kernel.cuh"
 #include "moc_decomp.cuh"
+#include "zonal_kernels.cuh"
 
 namespace cdfgpu {
 
@@ -414,6 +415,8 @@ int cdfgpu_finalize(void)
     cdfgpu_synchronize();
     cdfmoc_gpu_teardown();
     cdfmocsig_gpu_teardown();
+    cdfzonal_gpu_teardown();
+    cdfmhst_gpu_teardown();
     cudaStreamDestroy(g.s_compute);
     cudaStreamDestroy(g.s_copy);
     cudaStreamDestroy(g.s_d2h);
@@ -745,3 +748,4 @@ int cdfmoc_gpu_kernel_ms(int slot, float *ms)
 }  // extern "C"
 
 #include "api_mocsig.inc"
+#include "api_zonal.inc"

@@ -1,0 +1,180 @@
+// zonal_kernels.cuh -- K4 / K5: the masked zonal integral behind the sibling command lines.
+//   K4 zonal_rows_kernel   cdfzonalsum  (src/cdfzonalsum.f90:309-322)  and cdfzonalmean (src/cdfzonalmean.f90:312-344)
+//   K5 mhst_rows_kernel    cdfmhst      (src/cdfmhst.f90:303-366): vertical integral of the heat / salt transports,
+//                                       then the masked zonal sums
+// Both are HBM-streaming reductions like K1: coalesced loads, fp64 accumulation in registers, shuffle trees, no atomics
+// (bitwise reproducible).  The products follow the reference's types and association (REAL(4) or REAL(8) chains,
+// never contracted: the library is built with -fmad=false); only the order of the fp64 additions along i differs from
+// the reference's sequential loop.
+#pragma once
+#include "common.cuh"
+
+namespace cdfgpu {
+
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+
+// One warp per (level k, row j).  zmask is planar [NB][ny][nx]; out / omax / omin are [NB][nk][ny].
+//   MEAN = false: dtmp = dble(fl32(fl32(zmask*zmaskvar)*zv)); sum += dl_surf*dtmp; out = sum / alpha(j)
+//   MEAN = true : dtmp = ((1.d0*zmask)*zmaskvar)*zv in REAL(8); sum += dl_surf*dtmp; area += (dl_surf*zmask)*zmaskvar;
+//                 out = area /= 0 ? sum/area : zspval; lmax: max / min (non-zero) of dtmp as REAL(4), zspval where area == 0
+template <int NB, bool MEAN>
+__global__ void __launch_bounds__(256) zonal_rows_kernel(const float *__restrict__ zv, const float *__restrict__ mvar,
+                                                         const float *__restrict__ zmask, const double *__restrict__ dl,
+                                                         const float *__restrict__ alpha, int nx, int ny, int nk, float zspval,
+                                                         int lmax, double *__restrict__ out, float *__restrict__ omax,
+                                                         float *__restrict__ omin)
+{
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const size_t nrows = (size_t)nk * ny;
+    const size_t nxy = (size_t)nx * ny;
+    for (size_t r = (size_t)blockIdx.x * wpb + (threadIdx.x >> 5); r < nrows; r += (size_t)gridDim.x * wpb) {
+        const int k = (int)(r / ny), j = (int)(r - (size_t)k * ny);
+        const float *pv = zv + r * nx, *pm = mvar + r * nx;
+        const double *pd = dl + (size_t)j * nx;
+        const float *pz = zmask + (size_t)j * nx;
+        double acc[NB], area[MEAN ? NB : 1], dmax[MEAN ? NB : 1], dmin[MEAN ? NB : 1];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            acc[b] = 0.0;
+            if (MEAN) { area[b] = 0.0; dmax[b] = -INFINITY; dmin[b] = INFINITY; }
+        }
+#pragma unroll 2
+        for (int i = lane; i < nx; i += 32) {
+            const float v = __ldg(pv + i), mv = __ldg(pm + i);
+            const double d = __ldg(pd + i);
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const float m = __ldg(pz + (size_t)b * nxy + i);
+                if (!MEAN) {
+                    const float p = __fmul_rn(__fmul_rn(m, mv), v);
+                    acc[b] = __dadd_rn(acc[b], __dmul_rn(d, (double)p));
+                } else {
+                    const double dm = (double)m;
+                    const double dtmp = __dmul_rn(__dmul_rn(dm, (double)mv), (double)v);
+                    acc[b] = __dadd_rn(acc[b], __dmul_rn(d, dtmp));
+                    area[b] = __dadd_rn(area[b], __dmul_rn(__dmul_rn(d, dm), (double)mv));
+                    if (lmax) {   // NaN never wins a Fortran MAX/MIN started from a number: fmax / fmin behave the same
+                        dmax[b] = fmax(dmax[b], dtmp);
+                        if (dtmp != 0.0) dmin[b] = fmin(dmin[b], dtmp);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const double s = warp_sum(acc[b]);
+            const size_t o = ((size_t)b * nk + k) * ny + j;
+            if (!MEAN) {
+                if (lane == 0) out[o] = s / (double)(alpha ? alpha[j] : 1.0f);
+            } else {
+                const double a = warp_sum(area[b]);
+                if (lane == 0) out[o] = (a != 0.0) ? s / a : (double)zspval;
+                if (lmax) {
+                    const double mx = warp_max(dmax[b]), mn = warp_min(dmin[b]);
+                    if (lane == 0) {   // rzomax starts at -1.e20, rzomin at 1.e20 (REAL(4)); REAL(4) <- REAL(8) rounding is monotone
+                        omax[o] = (a == 0.0) ? zspval : (float)fmax((double)(-1.e20f), mx);
+                        omin[o] = (a == 0.0) ? zspval : (float)fmin((double)(1.e20f), mn);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// setup: dl_surf = (1.d0*e1)*e2 (cdfzonalsum.f90:257) and the basin planes (nb,nx,ny) basin-fastest -> planar [nb][ny][nx]
+__global__ void zonal_prep_kernel(const float *__restrict__ e1, const float *__restrict__ e2, const float *__restrict__ zmask_in,
+                                  int nb, size_t nxy, double *__restrict__ dl, float *__restrict__ zmask_planar)
+{
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < nxy; c += (size_t)gridDim.x * blockDim.x) {
+        dl[c] = __dmul_rn(__dmul_rn(1.0, (double)e1[c]), (double)e2[c]);
+        for (int b = 0; b < nb; ++b) zmask_planar[(size_t)b * nxy + c] = zmask_in[c * nb + b];
+    }
+}
+
+// K5: one CTA per latitude row j; a thread owns up to MAXC columns (i = tid + c*blockDim) and integrates them over the
+// levels in the reference's order:  dtrph += (dble(fl32(fl32(zvt*e1v)*e3v))*1000.)*4000. ; dtrps += dble(fl32(fl32(zvs*e1v)*e3v))
+// After the last level (every level with zdim) the masked zonal sums: global over i = 2..nx-1 with vmask(k=1), the basins
+// over all i.  masks: planar [4][ny][nx] (glo, atl, pac, ind; planes of absent basins are zero).  heat, salt: [nlev][4][ny].
+template <int MAXC>
+__global__ void __launch_bounds__(1024) mhst_rows_kernel(const float *__restrict__ zvt, const float *__restrict__ zvs,
+                                                         const float *__restrict__ e1v, const float *__restrict__ e3v,
+                                                         const float *__restrict__ masks, int nx, int ny, int nz, int zdim,
+                                                         int nmask, double *__restrict__ heat, double *__restrict__ salt)
+{
+    __shared__ double s_red[32][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const size_t nxy = (size_t)nx * ny;
+    for (int j = blockIdx.x; j < ny; j += gridDim.x) {
+        double th[MAXC], ts[MAXC];
+        float e1[MAXC];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            const int i = tid + c * blockDim.x;
+            th[c] = 0.0; ts[c] = 0.0;
+            e1[c] = (i < nx) ? __ldg(e1v + (size_t)j * nx + i) : 0.0f;
+        }
+        for (int k = 0; k < nz; ++k) {
+            const size_t base = (size_t)k * nxy + (size_t)j * nx;
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) {
+                const int i = tid + c * blockDim.x;
+                if (i < nx) {
+                    const float e3 = __ldg(e3v + base + i);
+                    const float h = __fmul_rn(__fmul_rn(__ldg(zvt + base + i), e1[c]), e3);
+                    const float s = __fmul_rn(__fmul_rn(__ldg(zvs + base + i), e1[c]), e3);
+                    th[c] = __dadd_rn(th[c], __dmul_rn(__dmul_rn((double)h, 1000.0), 4000.0));
+                    ts[c] = __dadd_rn(ts[c], (double)s);
+                }
+            }
+            if (zdim || k == nz - 1) {
+                double part[8];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    double sh = 0.0, ss = 0.0;
+                    if (m < nmask) {
+#pragma unroll
+                        for (int c = 0; c < MAXC; ++c) {
+                            const int i = tid + c * blockDim.x;
+                            const bool in = (m == 0) ? (i >= 1 && i < nx - 1) : (i < nx);
+                            if (in) {
+                                const double mk = (double)__ldg(masks + (size_t)m * nxy + (size_t)j * nx + i);
+                                sh = __dadd_rn(sh, __dmul_rn(th[c], mk));
+                                ss = __dadd_rn(ss, __dmul_rn(ts[c], mk));
+                            }
+                        }
+                    }
+                    part[2 * m] = warp_sum(sh);
+                    part[2 * m + 1] = warp_sum(ss);
+                }
+                __syncthreads();   // s_red of the previous level has been read
+                if (lane == 0) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) s_red[warp][q] = part[q];
+                }
+                __syncthreads();
+                if (tid < 8) {
+                    double t = 0.0;
+                    for (int w = 0; w < nwarps; ++w) t += s_red[w][tid];   // fixed order: deterministic
+                    const int lev = zdim ? k : 0, m = tid >> 1;
+                    double *dst = (tid & 1) ? salt : heat;
+                    dst[((size_t)lev * 4 + m) * ny + j] = t;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace cdfgpu

@@ -55,6 +55,15 @@ SIGNATURES = {
     "cdfmocsig_gpu_bins_device": (C.c_int, [C.c_void_p] * 4),
     "cdfmocsig_gpu_kernel_ms": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
     "cdfmocsig_gpu_teardown": (C.c_int, []),
+    "cdfzonal_gpu_setup": (C.c_int, [C.c_int] * 4 + [C.c_void_p] * 4),
+    "cdfzonal_gpu_sum": (C.c_int, [C.c_void_p] * 3),
+    "cdfzonal_gpu_mean": (C.c_int, [C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cdfzonal_gpu_kernel_ms": (C.c_int, [C.POINTER(C.c_float)]),
+    "cdfzonal_gpu_teardown": (C.c_int, []),
+    "cdfmhst_gpu_setup": (C.c_int, [C.c_int] * 3 + [C.c_void_p] * 6),
+    "cdfmhst_gpu_record": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "cdfmhst_gpu_kernel_ms": (C.c_int, [C.POINTER(C.c_float)]),
+    "cdfmhst_gpu_teardown": (C.c_int, []),
 }
 
 
@@ -289,3 +298,76 @@ def cdfmocsig_kernel_ms(slot: int) -> float:
 
 def cdfmocsig_teardown():
     _chk(load().cdfmocsig_gpu_teardown(), "cdfmocsig_gpu_teardown")
+
+
+# ---- sibling tools ----------------------------------------------------------------------
+def _c32(a):
+    a = np.ascontiguousarray(a, np.float32)
+    return a
+
+
+def cdfzonal_setup(e1, e2, zmask, zmaskvar):
+    """e1, e2 (ny,nx) f32; zmask (ny,nx,nb) f32 (basin fastest); zmaskvar (nk,ny,nx) f32."""
+    e1, e2, zmask, zmaskvar = _c32(e1), _c32(e2), _c32(zmask), _c32(zmaskvar)
+    nk, ny, nx = zmaskvar.shape
+    nb = zmask.shape[2]
+    assert e1.shape == (ny, nx) and e2.shape == (ny, nx) and zmask.shape[:2] == (ny, nx)
+    _chk(load().cdfzonal_gpu_setup(nx, ny, nk, nb, _ptr(e1), _ptr(e2), _ptr(zmask), _ptr(zmaskvar)), "cdfzonal_gpu_setup")
+    return nb, nk, ny
+
+
+def cdfzonal_sum(zv, shape, alpha=None):
+    """zv (nk,ny,nx) f32 -> dzosum (nb,nk,ny) f64; shape = the tuple cdfzonal_setup returned."""
+    zv = _c32(zv)
+    out = np.empty(shape, np.float64)
+    al = _c32(alpha) if alpha is not None else None
+    _chk(load().cdfzonal_gpu_sum(_ptr(zv), _ptr(al), _ptr(out)), "cdfzonal_gpu_sum")
+    return out
+
+
+def cdfzonal_mean(zv, shape, zspval=0.0, lmax=False):
+    """-> (dzomean (nb,nk,ny) f64, rzomax, rzomin (nb,nk,ny) f32 or None)."""
+    zv = _c32(zv)
+    mean = np.empty(shape, np.float64)
+    zmax = np.empty(shape, np.float32) if lmax else None
+    zmin = np.empty(shape, np.float32) if lmax else None
+    _chk(load().cdfzonal_gpu_mean(_ptr(zv), float(zspval), int(lmax), _ptr(mean), _ptr(zmax), _ptr(zmin)), "cdfzonal_gpu_mean")
+    return mean, zmax, zmin
+
+
+def cdfzonal_kernel_ms() -> float:
+    ms = C.c_float()
+    _chk(load().cdfzonal_gpu_kernel_ms(C.byref(ms)), "cdfzonal_gpu_kernel_ms")
+    return ms.value
+
+
+def cdfzonal_teardown():
+    _chk(load().cdfzonal_gpu_teardown(), "cdfzonal_gpu_teardown")
+
+
+def cdfmhst_setup(e1v, e3v, vmask1, atl=None, pac=None, ind=None):
+    e1v, e3v, vmask1 = _c32(e1v), _c32(e3v), _c32(vmask1)
+    nz, ny, nx = e3v.shape
+    a, p, i = (_c32(x) if x is not None else None for x in (atl, pac, ind))
+    _chk(load().cdfmhst_gpu_setup(nx, ny, nz, _ptr(e1v), _ptr(e3v), _ptr(vmask1), _ptr(a), _ptr(p), _ptr(i)), "cdfmhst_gpu_setup")
+    return nz, ny
+
+
+def cdfmhst_record(zvt, zvs, dims, zdim=False):
+    """zvt, zvs (nz,ny,nx) f32 -> heat, salt (nlev,4,ny) f64 raw zonal sums (glo, atl, pac, ind)."""
+    zvt, zvs = _c32(zvt), _c32(zvs)
+    nz, ny = dims
+    nlev = nz if zdim else 1
+    heat, salt = np.empty((nlev, 4, ny), np.float64), np.empty((nlev, 4, ny), np.float64)
+    _chk(load().cdfmhst_gpu_record(_ptr(zvt), _ptr(zvs), int(zdim), _ptr(heat), _ptr(salt)), "cdfmhst_gpu_record")
+    return heat, salt
+
+
+def cdfmhst_kernel_ms() -> float:
+    ms = C.c_float()
+    _chk(load().cdfmhst_gpu_kernel_ms(C.byref(ms)), "cdfmhst_gpu_kernel_ms")
+    return ms.value
+
+
+def cdfmhst_teardown():
+    _chk(load().cdfmhst_gpu_teardown(), "cdfmhst_gpu_teardown")

@@ -136,6 +136,37 @@ int cdfmocsig_gpu_bins_device(const float *d_zt, const float *d_zs, int32_t *d_i
 int cdfmocsig_gpu_kernel_ms(int slot, float *ms);
 int cdfmocsig_gpu_teardown(void);
 
+/* ---- sibling tools: the same masked zonal integral behind other command lines --------------
+ * Synchronous entry points on host buffers (pinned or pageable); one plan per tool and process.
+ *
+ * cdfzonalsum / cdfzonalmean -- replace the loop nests src/cdfzonalsum.f90:309-322 and src/cdfzonalmean.f90:312-344.
+ *   setup: e1, e2 (nx,ny) horizontal metrics of the variable's C-grid point (dl_surf = 1.d0*e1*e2, cdfzonalsum.f90:257);
+ *          zmask (nb,nx,ny) REAL(4) basin masks as assembled at cdfzonalsum.f90:286-296 (basin fastest);
+ *          zmaskvar (nx,ny,nk) the variable's mask, every level (read level by level at :306).
+ *   sum  : one 3-D record zv (nx,ny,nk) -> dzosum(ny,nk,nb) REAL(8) = SUM_i dl_surf*dble(zmask*zmaskvar*zv) / alpha(j)
+ *          (alpha (ny) REAL(4), the -pdeg normalisation of :260-265; NULL = 1).
+ *   mean : dzomean(ny,nk,nb) = SUM_i dl_surf*dtmp / SUM_i dl_surf*zmask*zmaskvar, zspval where the area is zero; with
+ *          lmax the zonal maximum and non-zero minimum of dtmp, rzomax / rzomin (ny,nk,nb) REAL(4) (:325-326,339-342). */
+int cdfzonal_gpu_setup(int nx, int ny, int nk, int nb, const float *e1, const float *e2, const float *zmask,
+                       const float *zmaskvar);
+int cdfzonal_gpu_sum(const float *zv, const float *alpha, double *dzosum);
+int cdfzonal_gpu_mean(const float *zv, float zspval, int lmax, double *dzomean, float *rzomax, float *rzomin);
+int cdfzonal_gpu_kernel_ms(float *ms); /* device time of the last sum / mean kernel */
+int cdfzonal_gpu_teardown(void);
+/* cdfmhst (-vt file mode) -- replaces src/cdfmhst.f90:303-366: vertical integral of vomevt / vomevs * e1v * e3v (heat
+ * scaled by pprau0*pprcp) followed by the masked zonal sums.
+ *   setup : e1v (nx,ny); e3v (nx,ny,nz) as read from the mesh file (or e31d(k) planes with -full); vmask1 = vmask(k=1);
+ *           atl, pac, ind (nx,ny) REAL(4) basin masks, or all three NULL when there is no basin file.
+ *   record: zvt, zvs (nx,ny,nz) -> heat, salt (ny,4,nlev) REAL(8): the raw sums dzonal_heat_* / dzonal_salt_* in the order
+ *           glo, atl, pac, ind (glo over i = 2..npiglo-1, :341-344); nlev = nz with zdim (the sums after every level,
+ *           :375) else 1 (after the last level).  The caller forms inp = ind + pac, inp0 = glo - atl, divides by 1.d15 /
+ *           1.d6 and replaces zeros by ppspval (:384-441). */
+int cdfmhst_gpu_setup(int nx, int ny, int nz, const float *e1v, const float *e3v, const float *vmask1, const float *atl,
+                      const float *pac, const float *ind);
+int cdfmhst_gpu_record(const float *zvt, const float *zvs, int zdim, double *heat, double *salt);
+int cdfmhst_gpu_kernel_ms(float *ms);
+int cdfmhst_gpu_teardown(void);
+
 #ifdef __cplusplus
 }
 #endif

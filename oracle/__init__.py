@@ -194,3 +194,75 @@ def cdfmoc_decomp_record(e1v, e1u, gphiv, gdept, e3m, ibmask, umask, tmask, zv, 
                                       _p(zt, C.c_float), _p(zs, C.c_float), _p(outs["total"], C.c_double),
                                       _p(outs["sh"], C.c_double), _p(outs["bt"], C.c_double), _p(outs["ag"], C.c_double))
     return outs
+
+
+# ---- sibling tools ---------------------------------------------------------------------
+def zonal_masks(msk1, atl=None, ind=None, pac=None):
+    """-> zmask (ny, nx, nb) float32, nb = 5 with basins else 1.  cdfzonalsum.f90:286-296."""
+    msk1 = _f32(msk1)
+    ny, nx = msk1.shape
+    nb = 5 if atl is not None else 1
+    out = np.zeros((ny, nx, nb), np.float32)
+    a, i, p_ = (_f32(x) if x is not None else None for x in (atl, ind, pac))
+    lib().oracle_zonal_masks(nx, ny, nb, _p(msk1, C.c_float), _p(a, C.c_float) if nb == 5 else None,
+                             _p(i, C.c_float) if nb == 5 else None, _p(p_, C.c_float) if nb == 5 else None,
+                             _p(out, C.c_float))
+    return out
+
+
+def zonal_dlsurf(e1, e2):
+    e1, e2 = _f32(e1), _f32(e2)
+    out = np.empty(e1.shape, np.float64)
+    lib().oracle_zonal_dlsurf(C.c_size_t(e1.size), _p(e1, C.c_float), _p(e2, C.c_float), _p(out, C.c_double))
+    return out
+
+
+def zonalsum_record(zmask, zmaskvar, zv, dl_surf, alpha=None):
+    """-> dzosum (nb, nk, ny) float64: every level of one record.  cdfzonalsum.f90:309-322."""
+    zmask, zmaskvar, zv = _f32(zmask), _f32(zmaskvar), _f32(zv)
+    dl = np.ascontiguousarray(dl_surf, np.float64)
+    nk, ny, nx = zv.shape
+    nb = zmask.shape[2]
+    al = _f32(alpha) if alpha is not None else None
+    out = np.empty((nb, nk, ny), np.float64)
+    tmp = np.empty((nb, ny), np.float64)
+    for k in range(nk):
+        lib().oracle_zonalsum_level(nx, ny, nb, _p(zmask, C.c_float), _p(zmaskvar[k], C.c_float), _p(zv[k], C.c_float),
+                                    _p(dl, C.c_double), _p(al, C.c_float) if al is not None else None, _p(tmp, C.c_double))
+        out[:, k, :] = tmp
+    return out
+
+
+def zonalmean_record(zmask, zmaskvar, zv, dl_surf, zspval=0.0, lmax=False):
+    """-> (mean (nb, nk, ny) f64, zmax, zmin (nb, nk, ny) f32 or None).  cdfzonalmean.f90:312-344."""
+    zmask, zmaskvar, zv = _f32(zmask), _f32(zmaskvar), _f32(zv)
+    dl = np.ascontiguousarray(dl_surf, np.float64)
+    nk, ny, nx = zv.shape
+    nb = zmask.shape[2]
+    mean = np.empty((nb, nk, ny), np.float64)
+    zmax = np.empty((nb, nk, ny), np.float32) if lmax else None
+    zmin = np.empty((nb, nk, ny), np.float32) if lmax else None
+    tm, ta, ti = np.empty((nb, ny), np.float64), np.empty((nb, ny), np.float32), np.empty((nb, ny), np.float32)
+    for k in range(nk):
+        lib().oracle_zonalmean_level(nx, ny, nb, _p(zmask, C.c_float), _p(zmaskvar[k], C.c_float), _p(zv[k], C.c_float),
+                                     _p(dl, C.c_double), C.c_float(zspval), int(lmax), _p(tm, C.c_double),
+                                     _p(ta, C.c_float), _p(ti, C.c_float))
+        mean[:, k, :] = tm
+        if lmax:
+            zmax[:, k, :] = ta
+            zmin[:, k, :] = ti
+    return mean, zmax, zmin
+
+
+def mhst_record(e1v, e3v, vmask1, zvt, zvs, atl=None, pac=None, ind=None, zdim=False):
+    """-> heat, salt (nlev, 4, ny) float64 raw zonal sums (glo, atl, pac, ind).  cdfmhst.f90:303-366."""
+    e1v, e3v, vmask1, zvt, zvs = _f32(e1v), _f32(e3v), _f32(vmask1), _f32(zvt), _f32(zvs)
+    nz, ny, nx = zvt.shape
+    assert e3v.shape == (nz, ny, nx)
+    nlev = nz if zdim else 1
+    heat, salt = np.empty((nlev, 4, ny), np.float64), np.empty((nlev, 4, ny), np.float64)
+    a, p_, i = (_f32(x) if x is not None else None for x in (atl, pac, ind))
+    ptr = lambda x: _p(x, C.c_float) if x is not None else None
+    lib().oracle_mhst_record(nx, ny, nz, _p(e1v, C.c_float), _p(e3v, C.c_float), _p(vmask1, C.c_float), ptr(a), ptr(p_), ptr(i),
+                             _p(zvt, C.c_float), _p(zvs, C.c_float), int(zdim), _p(heat, C.c_double), _p(salt, C.c_double))
+    return heat, salt

@@ -580,3 +580,143 @@ void oracle_decomp_zcoef(size_t n, const float *gphiv, float *zcoef)
         if (f != 0.f) { float g = -grav / rau0; zcoef[c] = g / f; } else zcoef[c] = 0.f;
     }
 }
+
+/* =============================================================================================
+ * Sibling tools: the same masked zonal integral behind other command lines.
+ * PARITY UNPINNED by the reference (no tests / golden vectors); pinned by the NumPy restatements in
+ * oracle/np_oracle.py and by property tests.
+ * ============================================================================================= */
+
+/* zonal basin masks of cdfzonalsum / cdfzonalmean -- src/cdfzonalsum.f90:286-296, cdfzonalmean.f90:287-297.
+ * REAL(4) planes: 1 global (the variable's mask at level 1), 2 atl, 4 ind, 5 pac, 3 = ind + pac clipped to 1.
+ * zmask(npbasins,npiglo,npjglo) -> zmask[(j*nx+i)*nb+b]; NO zeroing of the i=1 / i=nx columns here. */
+void oracle_zonal_masks(int nx, int ny, int nb, const float *msk1, const float *atl, const float *ind, const float *pac,
+                        float *zmask)
+{
+    for (size_t c = 0; c < (size_t)nx * ny; ++c) {
+        zmask[c * nb + 0] = msk1[c];
+        if (nb == 5) {
+            zmask[c * nb + 1] = atl[c];
+            zmask[c * nb + 3] = ind[c];
+            zmask[c * nb + 4] = pac[c];
+            float z = pac[c] + ind[c];
+            if (z > 0.0f) z = 1.0f;
+            zmask[c * nb + 2] = z;
+        }
+    }
+}
+
+/* dl_surf(:,:) = 1.d0 * e1(:,:) * e2(:,:) -- cdfzonalsum.f90:257, cdfzonalmean.f90:265: (1.d0*e1)*e2 in REAL(8) */
+void oracle_zonal_dlsurf(size_t n, const float *e1, const float *e2, double *dl)
+{
+    for (size_t c = 0; c < n; ++c) dl[c] = (1.0 * (double)e1[c]) * (double)e2[c];
+}
+
+/* cdfzonalsum, one level -- src/cdfzonalsum.f90:309-322.
+ *   dtmp = zmask(jbasin,ji,jj)*zmaskvar(ji,jj)*zv(ji,jj)*1.d0   : REAL(4) products left to right, then REAL(8)
+ *   dzosum(jj,jk) = dzosum(jj,jk) + dl_surf(ji,jj)*dtmp ; dzosum(:,jk) = dzosum(:,jk) / alpha(:)  (alpha REAL(4))
+ * out[b*ny + j] */
+void oracle_zonalsum_level(int nx, int ny, int nb, const float *zmask, const float *zmaskvar, const float *zv,
+                           const double *dl_surf, const float *alpha, double *out)
+{
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < ny; ++j)
+        for (int b = 0; b < nb; ++b) {
+            double acc = 0.0;
+            for (int i = 0; i < nx; ++i) {
+                const size_t c = (size_t)j * nx + i;
+                const float p1 = zmask[c * nb + b] * zmaskvar[c];
+                const float p2 = p1 * zv[c];
+                const double dtmp = (double)p2 * 1.0;
+                acc = acc + dl_surf[c] * dtmp;
+            }
+            out[(size_t)b * ny + j] = acc / (double)(alpha ? alpha[j] : 1.0f);
+        }
+}
+
+/* cdfzonalmean, one level -- src/cdfzonalmean.f90:312-344.
+ *   dtmp = 1.d0 * zmask*zmaskvar*zv                  : all REAL(8) (the first operand promotes the chain)
+ *   dzomean += dl_surf*dtmp ; darea += dl_surf*zmask*zmaskvar
+ *   lmax: rzomax = MAX(rzomax, dtmp) (REAL(4) <- REAL(8)), rzomin = MIN(rzomin, dtmp) where dtmp /= 0 ; start -1.e20 / 1.e20
+ *   mean = dzomean/darea where darea /= 0 else zspval ; rzomax = rzomin = zspval where darea == 0
+ * mean[b*ny+j], zmax/zmin[b*ny+j] (may be NULL when lmax == 0) */
+void oracle_zonalmean_level(int nx, int ny, int nb, const float *zmask, const float *zmaskvar, const float *zv,
+                            const double *dl_surf, float zspval, int lmax, double *mean, float *zmax, float *zmin)
+{
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < ny; ++j)
+        for (int b = 0; b < nb; ++b) {
+            double acc = 0.0, area = 0.0;
+            float rmax = -1.e20f, rmin = 1.e20f;
+            for (int i = 0; i < nx; ++i) {
+                const size_t c = (size_t)j * nx + i;
+                const double m = (double)zmask[c * nb + b];
+                const double dtmp = ((1.0 * m) * (double)zmaskvar[c]) * (double)zv[c];
+                acc = acc + dl_surf[c] * dtmp;
+                area = area + (dl_surf[c] * m) * (double)zmaskvar[c];
+                if (lmax) {
+                    const double a = (double)rmax;
+                    rmax = (float)(a > dtmp ? a : dtmp);   /* MAX(real4, real8): compared in REAL(8), stored REAL(4) */
+                    if (dtmp != 0.0) {
+                        const double bb = (double)rmin;
+                        rmin = (float)(bb < dtmp ? bb : dtmp);
+                    }
+                }
+            }
+            const size_t o = (size_t)b * ny + j;
+            mean[o] = (area != 0.0) ? acc / area : (double)zspval;
+            if (lmax) {
+                zmax[o] = (area == 0.0) ? zspval : rmax;
+                zmin[o] = (area == 0.0) ? zspval : rmin;
+            }
+        }
+}
+
+/* cdfmhst, one record (-vt file mode) -- src/cdfmhst.f90:303-366.
+ *   dwkh = zvt*e1v*e3v*1.d0 (REAL(4) products, then REAL(8)) ; dtrph += dwkh*pprau0*pprcp (1000., 4000. REAL(4) constants)
+ *   dwks likewise ; dtrps += dwks
+ *   zonal sums after each level: global SUM(dtrph(2:npiglo-1,jj)*vmask1(2:npiglo-1,jj)); atl / pac / ind over all i.
+ * heat, salt: [nlev][4][ny] with nlev = nz (zdim: cumulative after each level) or 1 (after the last level);
+ * basin order glo, atl, pac, ind; atl/pac/ind may be NULL (then only glo is written, the others are 0). */
+void oracle_mhst_record(int nx, int ny, int nz, const float *e1v, const float *e3v, const float *vmask1, const float *atl,
+                        const float *pac, const float *ind, const float *zvt, const float *zvs, int zdim, double *heat,
+                        double *salt)
+{
+    const size_t nxy = (size_t)nx * ny;
+    double *dtrph = (double *)calloc(nxy, sizeof(double)), *dtrps = (double *)calloc(nxy, sizeof(double));
+    const float *masks[4] = {vmask1, atl, pac, ind};
+    const int nlev = zdim ? nz : 1;
+    memset(heat, 0, sizeof(double) * nlev * 4 * ny);
+    memset(salt, 0, sizeof(double) * nlev * 4 * ny);
+    for (int k = 0; k < nz; ++k) {
+#pragma omp parallel for schedule(static)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                const size_t c = (size_t)j * nx + i, c3 = (size_t)k * nxy + c;
+                const float h1 = zvt[c3] * e1v[c], h2 = h1 * e3v[c3];
+                const float s1 = zvs[c3] * e1v[c], s2 = s1 * e3v[c3];
+                const double dwkh = (double)h2 * 1.0, dwks = (double)s2 * 1.0;
+                dtrph[c] = dtrph[c] + (dwkh * (double)1000.0f) * (double)4000.0f;
+                dtrps[c] = dtrps[c] + dwks;
+            }
+        if (zdim || k == nz - 1) {
+            const int lev = zdim ? k : 0;
+#pragma omp parallel for schedule(static)
+            for (int j = 0; j < ny; ++j)
+                for (int m = 0; m < 4; ++m) {
+                    if (!masks[m]) continue;
+                    const int i0 = (m == 0) ? 1 : 0, i1 = (m == 0) ? nx - 1 : nx;
+                    double sh = 0.0, ss = 0.0;
+                    for (int i = i0; i < i1; ++i) {
+                        const size_t c = (size_t)j * nx + i;
+                        sh = sh + dtrph[c] * (double)masks[m][c];
+                        ss = ss + dtrps[c] * (double)masks[m][c];
+                    }
+                    heat[((size_t)lev * 4 + m) * ny + j] = sh;
+                    salt[((size_t)lev * 4 + m) * ny + j] = ss;
+                }
+        }
+    }
+    free(dtrph);
+    free(dtrps);
+}

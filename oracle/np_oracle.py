@@ -289,3 +289,67 @@ def cdfmoc_decomp_record(e1v, e1u, gphiv, gdept, e3m, ibmask, umask, tmask, zv, 
         dvbt = np.where(hdep != 0, dvbt / np.where(hdep != 0, hdep, 1).astype(f8), 0.0)
     sh = scan(sh - weighted(dvbt))
     return {"total": total, "sh": sh, "bt": bt, "ag": total - sh - bt}
+
+
+# ---- sibling tools: independent NumPy restatements ----------------------------------------
+f4, f8 = np.float32, np.float64
+
+def zonalsum_record(zmask, zmaskvar, zv, e1, e2, alpha=None):
+    """cdfzonalsum.f90:257,309-322.  zmask (ny,nx,nb) f32, zmaskvar / zv (nk,ny,nx) f32 -> (nb,nk,ny) f64."""
+    dl = (f8(1.0) * e1.astype(f8)) * e2.astype(f8)
+    nk, ny, nx = zv.shape
+    nb = zmask.shape[2]
+    out = np.empty((nb, nk, ny), f8)
+    al = np.ones(ny, f4) if alpha is None else alpha.astype(f4)
+    for b in range(nb):
+        for k in range(nk):
+            p = ((zmask[:, :, b] * zmaskvar[k]).astype(f4) * zv[k]).astype(f4).astype(f8)
+            out[b, k] = np.cumsum(dl * p, axis=1)[:, -1] / al.astype(f8)   # cumsum: sequential in i like the DO loop
+    return out
+
+
+def zonalmean_record(zmask, zmaskvar, zv, e1, e2, zspval=0.0, lmax=False):
+    """cdfzonalmean.f90:265,312-344 -> mean (nb,nk,ny) f64, zmax, zmin (nb,nk,ny) f32 (None without lmax)."""
+    dl = (f8(1.0) * e1.astype(f8)) * e2.astype(f8)
+    nk, ny, nx = zv.shape
+    nb = zmask.shape[2]
+    mean = np.empty((nb, nk, ny), f8)
+    zmax = np.empty((nb, nk, ny), f4) if lmax else None
+    zmin = np.empty((nb, nk, ny), f4) if lmax else None
+    for b in range(nb):
+        m = zmask[:, :, b].astype(f8)
+        for k in range(nk):
+            dtmp = ((f8(1.0) * m) * zmaskvar[k].astype(f8)) * zv[k].astype(f8)
+            acc = np.cumsum(dl * dtmp, axis=1)[:, -1]
+            area = np.cumsum((dl * m) * zmaskvar[k].astype(f8), axis=1)[:, -1]
+            with np.errstate(all="ignore"):
+                mean[b, k] = np.where(area != 0, acc / np.where(area != 0, area, 1.0), f8(f4(zspval)))
+            if lmax:
+                mx = np.maximum(f8(f4(-1.e20)), dtmp.max(axis=1)).astype(f4)
+                mn = np.minimum(f8(f4(1.e20)), np.where(dtmp != 0, dtmp, np.inf).min(axis=1)).astype(f4)
+                zmax[b, k] = np.where(area == 0, f4(zspval), mx)
+                zmin[b, k] = np.where(area == 0, f4(zspval), mn)
+    return mean, zmax, zmin
+
+
+def mhst_record(e1v, e3v, vmask1, zvt, zvs, atl=None, pac=None, ind=None, zdim=False):
+    """cdfmhst.f90:303-366 -> heat, salt (nlev,4,ny) f64 raw zonal sums, order glo, atl, pac, ind."""
+    nz, ny, nx = zvt.shape
+    nlev = nz if zdim else 1
+    heat, salt = np.zeros((nlev, 4, ny), f8), np.zeros((nlev, 4, ny), f8)
+    dtrph, dtrps = np.zeros((ny, nx), f8), np.zeros((ny, nx), f8)
+    masks = [vmask1, atl, pac, ind]
+    for k in range(nz):
+        dwkh = ((zvt[k] * e1v).astype(f4) * e3v[k]).astype(f4).astype(f8)
+        dwks = ((zvs[k] * e1v).astype(f4) * e3v[k]).astype(f4).astype(f8)
+        dtrph = dtrph + (dwkh * f8(f4(1000.0))) * f8(f4(4000.0))
+        dtrps = dtrps + dwks
+        if zdim or k == nz - 1:
+            lev = k if zdim else 0
+            for m, mk in enumerate(masks):
+                if mk is None:
+                    continue
+                sl = slice(1, nx - 1) if m == 0 else slice(0, nx)
+                heat[lev, m] = np.cumsum(dtrph[:, sl] * mk[:, sl].astype(f8), axis=1)[:, -1]
+                salt[lev, m] = np.cumsum(dtrps[:, sl] * mk[:, sl].astype(f8), axis=1)[:, -1]
+    return heat, salt
