@@ -28,9 +28,12 @@ __device__ __forceinline__ double warp_min(double v)
 //   MEAN = false: dtmp = dble(fl32(fl32(zmask*zmaskvar)*zv)); sum += dl_surf*dtmp; out = sum / alpha(j)
 //   MEAN = true : dtmp = ((1.d0*zmask)*zmaskvar)*zv in REAL(8); sum += dl_surf*dtmp; area += (dl_surf*zmask)*zmaskvar;
 //                 out = area /= 0 ? sum/area : zspval; lmax: max / min (non-zero) of dtmp as REAL(4), zspval where area == 0
-template <int NB, bool MEAN>
+// BITS: every basin mask value is exactly 0 or 1 (checked at setup): one byte per (j,i) holds the NB mask bits; the bit is
+// decoded to 0.f / 1.f and multiplied as the reference does (so NaN / Inf data behave identically).
+template <int NB, bool MEAN, bool BITS>
 __global__ void __launch_bounds__(256) zonal_rows_kernel(const float *__restrict__ zv, const float *__restrict__ mvar,
-                                                         const float *__restrict__ zmask, const double *__restrict__ dl,
+                                                         const float *__restrict__ zmask, const uint8_t *__restrict__ zbits,
+                                                         const double *__restrict__ dl,
                                                          const float *__restrict__ alpha, int nx, int ny, int nk, float zspval,
                                                          int lmax, double *__restrict__ out, float *__restrict__ omax,
                                                          float *__restrict__ omin)
@@ -44,19 +47,21 @@ __global__ void __launch_bounds__(256) zonal_rows_kernel(const float *__restrict
         const float *pv = zv + r * nx, *pm = mvar + r * nx;
         const double *pd = dl + (size_t)j * nx;
         const float *pz = zmask + (size_t)j * nx;
+        const uint8_t *pb = zbits + (size_t)j * nx;
         double acc[NB], area[MEAN ? NB : 1], dmax[MEAN ? NB : 1], dmin[MEAN ? NB : 1];
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             acc[b] = 0.0;
             if (MEAN) { area[b] = 0.0; dmax[b] = -INFINITY; dmin[b] = INFINITY; }
         }
-#pragma unroll 2
+#pragma unroll 4
         for (int i = lane; i < nx; i += 32) {
             const float v = __ldg(pv + i), mv = __ldg(pm + i);
             const double d = __ldg(pd + i);
+            const unsigned bits = BITS ? (unsigned)__ldg(pb + i) : 0u;
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
-                const float m = __ldg(pz + (size_t)b * nxy + i);
+                const float m = BITS ? (((bits >> b) & 1u) ? 1.0f : 0.0f) : __ldg(pz + (size_t)b * nxy + i);
                 if (!MEAN) {
                     const float p = __fmul_rn(__fmul_rn(m, mv), v);
                     acc[b] = __dadd_rn(acc[b], __dmul_rn(d, (double)p));
