@@ -43,8 +43,11 @@ __global__ void __launch_bounds__(256) zonal_rows_kernel(const float *__restrict
     const size_t nrows = (size_t)nk * ny;
     const size_t nxy = (size_t)nx * ny;
     for (size_t r = (size_t)blockIdx.x * wpb + (threadIdx.x >> 5); r < nrows; r += (size_t)gridDim.x * wpb) {
-        const int k = (int)(r / ny), j = (int)(r - (size_t)k * ny);
-        const float *pv = zv + r * nx, *pm = mvar + r * nx;
+        // level fastest: the warps of a CTA work on the same latitude row, so dl_surf and the mask bytes of that row are
+        // read from L2 once and then hit in L1
+        const int j = (int)(r / nk), k = (int)(r - (size_t)j * nk);
+        const size_t row = (size_t)k * ny + j;
+        const float *pv = zv + row * nx, *pm = mvar + row * nx;
         const double *pd = dl + (size_t)j * nx;
         const float *pz = zmask + (size_t)j * nx;
         const uint8_t *pb = zbits + (size_t)j * nx;
@@ -59,9 +62,36 @@ __global__ void __launch_bounds__(256) zonal_rows_kernel(const float *__restrict
             const float v = __ldg(pv + i), mv = __ldg(pm + i);
             const double d = __ldg(pd + i);
             const unsigned bits = BITS ? (unsigned)__ldg(pb + i) : 0u;
+            if (BITS) {
+                // mask values are 0 or 1: the per-basin product chain has only two possible values, the one of a 1 and the
+                // one of a 0 (a signed zero, or NaN when the data are not finite) -- form both once, select per basin
+                if (!MEAN) {
+                    const double t1 = __dmul_rn(d, (double)__fmul_rn(__fmul_rn(1.0f, mv), v));
+                    const double t0 = __dmul_rn(d, (double)__fmul_rn(__fmul_rn(0.0f, mv), v));
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) acc[b] = __dadd_rn(acc[b], ((bits >> b) & 1u) ? t1 : t0);
+                } else {
+                    const double dmv = (double)mv, dv = (double)v;
+                    const double x1 = __dmul_rn(__dmul_rn(1.0, dmv), dv), x0 = __dmul_rn(__dmul_rn(0.0, dmv), dv);
+                    const double t1 = __dmul_rn(d, x1), t0 = __dmul_rn(d, x0);
+                    const double a1 = __dmul_rn(__dmul_rn(d, 1.0), dmv), a0 = __dmul_rn(__dmul_rn(d, 0.0), dmv);
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        const bool on = ((bits >> b) & 1u) != 0u;
+                        const double dtmp = on ? x1 : x0;
+                        acc[b] = __dadd_rn(acc[b], on ? t1 : t0);
+                        area[b] = __dadd_rn(area[b], on ? a1 : a0);
+                        if (lmax) {
+                            dmax[b] = fmax(dmax[b], dtmp);
+                            if (dtmp != 0.0) dmin[b] = fmin(dmin[b], dtmp);
+                        }
+                    }
+                }
+                continue;
+            }
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
-                const float m = BITS ? (((bits >> b) & 1u) ? 1.0f : 0.0f) : __ldg(pz + (size_t)b * nxy + i);
+                const float m = __ldg(pz + (size_t)b * nxy + i);
                 if (!MEAN) {
                     const float p = __fmul_rn(__fmul_rn(m, mv), v);
                     acc[b] = __dadd_rn(acc[b], __dmul_rn(d, (double)p));
