@@ -52,6 +52,22 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4 *p, uint64_t pol)
     return r;
 }
 
+// asynchronous global -> shared copies (LDGSTS): no registers are held while the data are in flight
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
