@@ -63,7 +63,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 HOST = CSRC / "host"
-HOST_TOOLS = {"cdfmoc_gpu": "cdfmoc_main.cpp", "cdfmocsig_gpu": "cdfmocsig_main.cpp", "nc3dump": "nc3dump_main.cpp"}
+HOST_TOOLS = {"cdfmoc_gpu": "cdfmoc_main.cpp", "cdfmocsig_gpu": "cdfmocsig_main.cpp", "cdfmhst_gpu": "cdfmhst_main.cpp",
+              "nc3dump": "nc3dump_main.cpp"}
 
 
 def build_host(force: bool = False) -> dict:

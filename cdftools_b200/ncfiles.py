@@ -89,3 +89,23 @@ def write_gridt(m: synth.Mesh, path, nrec, spval=0.0, version=2):
         recs.append((tt, ss))
     f.close()
     return recs
+
+
+def write_vt(m: synth.Mesh, path, nrec, version=2):
+    """VT file as cdfvT writes it: vomevt, vomevs (time_counter, depthv, y, x) f32 (only the V components are needed)."""
+    nz, ny, nx = m.e3v_0.shape
+    f = _new(path, {"x": nx, "y": ny, "depthv": nz, "time_counter": None}, version)
+    tc = f.createVariable("time_counter", "d", ("time_counter",))
+    vt = f.createVariable("vomevt", "f", ("time_counter", "depthv", "y", "x"))
+    vs = f.createVariable("vomevs", "f", ("time_counter", "depthv", "y", "x"))
+    recs = []
+    for r in range(nrec):
+        tc[r] = 432000.0 * (r + 0.5)
+        v = synth.make_v_record(m, r)
+        t, s = synth.make_ts_record(m, r)
+        a, b = (v * t).astype(np.float32), (v * s).astype(np.float32)
+        vt[r] = a
+        vs[r] = b
+        recs.append((a, b))
+    f.close()
+    return recs
