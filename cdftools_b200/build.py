@@ -64,7 +64,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 HOST = CSRC / "host"
 HOST_TOOLS = {"cdfmoc_gpu": "cdfmoc_main.cpp", "cdfmocsig_gpu": "cdfmocsig_main.cpp", "cdfmhst_gpu": "cdfmhst_main.cpp",
-              "nc3dump": "nc3dump_main.cpp"}
+              "cdfzonalsum_gpu": "cdfzonal_main.cpp", "cdfzonalmean_gpu": "cdfzonal_main.cpp", "nc3dump": "nc3dump_main.cpp"}
+HOST_DEFINES = {"cdfzonalmean_gpu": ["-DZONAL_MEAN"]}
 
 
 def build_host(force: bool = False) -> dict:
@@ -79,7 +80,7 @@ def build_host(force: bool = False) -> dict:
         exe = bindir / name
         deps = [HOST / src] + hdrs + ([SO] if name != "nc3dump" else [])
         if force or not exe.exists() or any(d.stat().st_mtime > exe.stat().st_mtime for d in deps):
-            cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-ffp-contract=off", "-o", str(exe), str(HOST / src)]
+            cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-ffp-contract=off", *HOST_DEFINES.get(name, []), "-o", str(exe), str(HOST / src)]
             if name != "nc3dump":
                 cmd += ["-L" + str(PKG), "-lcdfgpu", "-Wl,-rpath," + str(PKG), "-Wl,-rpath,$ORIGIN/.."]
             r = subprocess.run(cmd, capture_output=True, text=True)

@@ -24,7 +24,8 @@ def write_mesh(m: synth.Mesh, outdir, with_basins=True, version=2):
     out.mkdir(parents=True, exist_ok=True)
     nz, ny, nx = m.e3v_0.shape
     f = _new(out / "mesh_hgr.nc", {"x": nx, "y": ny, "t": None}, version)
-    for name, arr in (("e1v", m.e1v), ("e1u", m.e1u), ("gphiv", m.gphiv), ("glamv", m.glamv)):
+    e2v = (m.e1v * np.float32(0.75)).astype(np.float32)   # the synthetic mesh carries no e2v: any positive field will do
+    for name, arr in (("e1v", m.e1v), ("e1u", m.e1u), ("e2v", e2v), ("gphiv", m.gphiv), ("glamv", m.glamv)):
         v = f.createVariable(name, "f", ("t", "y", "x"))
         v[0] = arr
     f.close()
