@@ -548,6 +548,29 @@ __device__ __noinline__ int sigma_bin_slow(float tem, float sal, float sigmin, f
     return min(max(ib, 1), nbins);
 }
 
+// Bins of the 8 cells of a group (scrubbed T, S; `need` = the cells whose bin is wanted): the production bin function.
+// Fast path in batches of kSigEosBatch cells, the reference chain for the cells it does not vouch for.  The fused kernel
+// and the diagnostic kernel behind cdfmocsig_gpu_bins_device (bit-exact sweep in the parity tests) both call this.
+template <int EOS, bool SIGMA0>
+__device__ __forceinline__ void sig_group_bins(const float *tt, const float *sv, unsigned need, const SigParams &p, int *ib)
+{
+    unsigned bad = 0xffu;
+    if (EOS != CDFGPU_EOS_NEUTRAL && p.qmargin >= 0.0) {
+        unsigned ok = 0u;
+#pragma unroll
+        for (int c0 = 0; c0 < 8; c0 += kSigEosBatch)
+            ok |= sigma_bins_try<SIGMA0, kSigEosBatch>(tt + c0, sv + c0, p, ib + c0) << c0;
+        bad = ~ok & 0xffu;
+    }
+    bad &= need;
+    if (bad) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (bad & (1u << c))
+                ib[c] = sigma_bin_slow<EOS, SIGMA0>(tt[c], sv[c], p.sigmin, p.sigstp, p.sps, p.nbins, p.dlh, p.dlref);
+    }
+}
+
 // hist_flush with a shortcut for a single live lane (a bin boundary inside one lane's group)
 __device__ __forceinline__ void hist_flush_few(double *hist, int key, double val, int lane)
 {
@@ -675,7 +698,7 @@ __device__ __forceinline__ void sig_dense_compute(const SigParams &p, const SigQ
 #pragma unroll
     for (int c = 0; c < 8; ++c) { key[c] = -1; pr[c] = 0.0f; }
     if (D.active) {
-        const unsigned need = D.d.y & 255u;
+        unsigned need = D.d.y & 255u;
         float tt[8], sv[8];
         tt[0] = D.ta.x; tt[1] = D.ta.y; tt[2] = D.ta.z; tt[3] = D.ta.w; tt[4] = D.tb.x; tt[5] = D.tb.y; tt[6] = D.tb.z; tt[7] = D.tb.w;
         sv[0] = D.sa.x; sv[1] = D.sa.y; sv[2] = D.sa.z; sv[3] = D.sa.w; sv[4] = D.sb.x; sv[5] = D.sb.y; sv[6] = D.sb.z; sv[7] = D.sb.w;
@@ -687,26 +710,20 @@ __device__ __forceinline__ void sig_dense_compute(const SigParams &p, const SigQ
             for (int c = 0; c < 8; ++c) { tt[c] = scrub(tt[c], p.spt); sv[c] = scrub(sv[c], p.sps); }
         }
         if (ISO) {
+            // -isodep queues every covered cell; those that are masked (itmask = 0), carry no transport and have a finite
+            // area add exact zeros to all three histograms: drop them before the EOS (the dry cells below the sea floor)
+            const float4 qa = q.pa[D.slot], qb = q.pb[D.slot];
+            pr[0] = qa.x; pr[1] = qa.y; pr[2] = qa.z; pr[3] = qa.w; pr[4] = qb.x; pr[5] = qb.y; pr[6] = qb.z; pr[7] = qb.w;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) ss[c] = sv[c];
+            for (int c = 0; c < 8; ++c) {
+                ss[c] = sv[c];
+                const bool finite_area = (__float_as_uint(ar[c]) & 0x7f800000u) != 0x7f800000u;
+                if (sv[c] == p.sps && pr[c] == 0.0f && finite_area) need &= ~(1u << c);
+            }
         }
         int ib[8];
-        unsigned bad = 0xffu;
-        if (EOS != CDFGPU_EOS_NEUTRAL && p.qmargin >= 0.0) {
-            unsigned ok = 0u;
-#pragma unroll
-            for (int c0 = 0; c0 < 8; c0 += kSigEosBatch)
-                ok |= sigma_bins_try<SIGMA0, kSigEosBatch>(tt + c0, sv + c0, p, ib + c0) << c0;
-            bad = ~ok & 0xffu;
-        }
-        bad &= need;
-        if (bad) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-                if (bad & (1u << c))
-                    ib[c] = sigma_bin_slow<EOS, SIGMA0>(tt[c], sv[c], p.sigmin, p.sigstp, p.sps, p.nbins, p.dlh, p.dlref);
-        }
-        {
+        sig_group_bins<EOS, SIGMA0>(tt, sv, need, p, ib);
+        if (!ISO) {
             const float4 qa = q.pa[D.slot], qb = q.pb[D.slot];
             pr[0] = qa.x; pr[1] = qa.y; pr[2] = qa.z; pr[3] = qa.w; pr[4] = qb.x; pr[5] = qb.y; pr[6] = qb.z; pr[7] = qb.w;
         }
@@ -923,12 +940,29 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
     }
 }
 
-// Diagnostic kernel for the parity tests: ibin of every cell of a record, same device function as the fused kernel.
+// Diagnostic kernel for the parity tests: ibin of every cell of a record, through the same group function as the fused
+// kernel (8 consecutive cells per thread).
 template <int EOS, bool SIGMA0>
-__global__ void mocsig_bins_kernel(const SigParams p, int32_t *__restrict__ ibin, size_t n)
+__global__ void mocsig_bins_kernel(const __grid_constant__ SigParams p, int32_t *__restrict__ ibin, size_t n)
 {
-    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x)
-        ibin[c] = sigma_bin_fast<EOS, SIGMA0>(scrub(p.zt[c], p.spt), scrub(p.zs[c], p.sps), p);
+    const size_t ngroups = (n + 7) / 8;
+    for (size_t g8 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g8 < ngroups; g8 += (size_t)gridDim.x * blockDim.x) {
+        float tt[8], sv[8];
+        int ib[8];
+        unsigned need = 0u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const size_t e = g8 * 8 + c;
+            const bool in = e < n;
+            tt[c] = scrub(in ? p.zt[e] : 0.0f, p.spt);
+            sv[c] = scrub(in ? p.zs[e] : 0.0f, p.sps);
+            if (in) need |= 1u << c;
+        }
+        sig_group_bins<EOS, SIGMA0>(tt, sv, need, p, ib);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (need & (1u << c)) ibin[g8 * 8 + c] = ib[c];
+    }
 }
 
 // setup kernel: area = fl32(e1v * e3v) (cdfmocsig.f90:390), e3v NOT masked.

@@ -19,7 +19,12 @@ z = torch.from_numpy(m.gdept_1d[:-1].astype(np.float32)).cuda()[:, None, None]
 cl = torch.cos(torch.deg2rad(torch.from_numpy(m.gphiv).cuda()))[None]
 nbins, smin, sstp = {0.0: (104, 23.0, 0.05), 2000.0: (158, 30.0, 0.05), 1000.0: (88, 24.0, 0.1)}[pref]
 nbins = int(os.environ.get('NBINS', nbins))
-lib.cdfmocsig_setup(m.e1v, m.e3v_0, ib, m.nz, nbins, smin, sstp, pref, 0)
+eos = int(os.environ.get('EOS', 0))   # 0 EOS80, 1 TEOS10, 2 neutral density
+if eos == 2:
+    nbins, smin, sstp = oracle.default_bins(0.0, True)
+lib.cdfmocsig_setup(m.e1v, m.e3v_0, ib, m.nz, nbins, smin, sstp, pref, eos)
+if os.environ.get('ISO'):
+    lib.cdfmocsig_set_isodep(m.gdept_1d)
 st = torch.cuda.Stream()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 cells = m.nx * m.ny * m.nz
@@ -39,7 +44,7 @@ for noise in (0.0, 0.15):
         e1.record(st)
     st.synchronize()
     ms = e0.elapsed_time(e1) / 8
-    print(json.dumps({"kernel": "K2", "grid": grid, "pref": pref, "nbins": nbins, "noise": noise, "ms_per_record": round(ms, 4),
+    print(json.dumps({"kernel": "K2", "grid": grid, "pref": pref, "nbins": nbins, "eos": eos, "iso": bool(os.environ.get("ISO")), "noise": noise, "ms_per_record": round(ms, 4),
                       "cells_per_s": cells / ms * 1e3, "checksum": float(o2.abs().sum().item())}))
     del trec, srec
 lib.cdfmocsig_teardown()
