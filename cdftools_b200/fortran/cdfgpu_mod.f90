@@ -162,6 +162,52 @@ MODULE cdfgpu
      INTEGER(C_INT) FUNCTION cdfmocsig_gpu_teardown() BIND(C, NAME='cdfmocsig_gpu_teardown')
        IMPORT :: C_INT
      END FUNCTION cdfmocsig_gpu_teardown
+     ! ---- sibling tools: cdfzonalsum / cdfzonalmean / cdfmhst (include/cdfgpu.h, SURVEY 8 f3) ----
+     INTEGER(C_INT) FUNCTION cdfzonal_gpu_setup(nx, ny, nk, nb, e1, e2, zmask, zmaskvar) BIND(C, NAME='cdfzonal_gpu_setup')
+       IMPORT :: C_INT, C_FLOAT
+       INTEGER(C_INT), VALUE :: nx, ny, nk, nb
+       REAL(C_FLOAT), INTENT(in) :: e1(*), e2(*)            ! (npiglo,npjglo) metrics of the variable's grid point
+       REAL(C_FLOAT), INTENT(in) :: zmask(*)                ! (npbasins,npiglo,npjglo), cdfzonalsum.f90:286-296
+       REAL(C_FLOAT), INTENT(in) :: zmaskvar(*)             ! (npiglo,npjglo,npk) mask of the variable, every level
+     END FUNCTION cdfzonal_gpu_setup
+
+     INTEGER(C_INT) FUNCTION cdfzonal_gpu_sum(zv, alpha, dzosum) BIND(C, NAME='cdfzonal_gpu_sum')
+       IMPORT :: C_INT, C_FLOAT, C_DOUBLE, C_PTR
+       REAL(C_FLOAT), INTENT(in) :: zv(*)                   ! (npiglo,npjglo,npk) one record of one variable
+       TYPE(C_PTR), VALUE :: alpha                          ! C_LOC(alpha(npjglo)) with -pdeg, else C_NULL_PTR
+       REAL(C_DOUBLE), INTENT(out) :: dzosum(*)             ! (npjglo,npk,npbasins)
+     END FUNCTION cdfzonal_gpu_sum
+
+     INTEGER(C_INT) FUNCTION cdfzonal_gpu_mean(zv, zspval, lmax, dzomean, rzomax, rzomin) BIND(C, NAME='cdfzonal_gpu_mean')
+       IMPORT :: C_INT, C_FLOAT, C_DOUBLE, C_PTR
+       REAL(C_FLOAT), INTENT(in) :: zv(*)
+       REAL(C_FLOAT), VALUE :: zspval
+       INTEGER(C_INT), VALUE :: lmax                        ! 1 with -max
+       REAL(C_DOUBLE), INTENT(out) :: dzomean(*)            ! (npjglo,npk,npbasins)
+       TYPE(C_PTR), VALUE :: rzomax, rzomin                 ! C_LOC of (npjglo,npk,npbasins) REAL(4), or C_NULL_PTR
+     END FUNCTION cdfzonal_gpu_mean
+
+     INTEGER(C_INT) FUNCTION cdfzonal_gpu_teardown() BIND(C, NAME='cdfzonal_gpu_teardown')
+       IMPORT :: C_INT
+     END FUNCTION cdfzonal_gpu_teardown
+
+     INTEGER(C_INT) FUNCTION cdfmhst_gpu_setup(nx, ny, nz, e1v, e3v, vmask1, atl, pac, ind) BIND(C, NAME='cdfmhst_gpu_setup')
+       IMPORT :: C_INT, C_FLOAT, C_PTR
+       INTEGER(C_INT), VALUE :: nx, ny, nz
+       REAL(C_FLOAT), INTENT(in) :: e1v(*), e3v(*), vmask1(*)   ! e3v (npiglo,npjglo,npk) as read (cdfmhst.f90:331-334)
+       TYPE(C_PTR), VALUE :: atl, pac, ind                  ! C_LOC of the basin masks, or all C_NULL_PTR
+     END FUNCTION cdfmhst_gpu_setup
+
+     INTEGER(C_INT) FUNCTION cdfmhst_gpu_record(zvt, zvs, zdim, heat, salt) BIND(C, NAME='cdfmhst_gpu_record')
+       IMPORT :: C_INT, C_FLOAT, C_DOUBLE
+       REAL(C_FLOAT), INTENT(in) :: zvt(*), zvs(*)          ! (npiglo,npjglo,npk)
+       INTEGER(C_INT), VALUE :: zdim                        ! 1 with -Zdim
+       REAL(C_DOUBLE), INTENT(out) :: heat(*), salt(*)      ! (npjglo,4,nlev): glo, atl, pac, ind raw zonal sums
+     END FUNCTION cdfmhst_gpu_record
+
+     INTEGER(C_INT) FUNCTION cdfmhst_gpu_teardown() BIND(C, NAME='cdfmhst_gpu_teardown')
+       IMPORT :: C_INT
+     END FUNCTION cdfmhst_gpu_teardown
   END INTERFACE
 
 CONTAINS
