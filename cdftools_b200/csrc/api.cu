@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "moc_kernel.cuh"
 #include "moc_kernel_tma.cuh"
+#include "moc_kernel_pipe.cuh"
 #include "mocsig_kernel.cuh"
 #include "moc_decomp.cuh"
 #include "zonal_kernels.cuh"
@@ -228,9 +229,34 @@ static int moc_launch_v(const MocParams &p, cudaStream_t st)
     ++g.launches;
     return CDFGPU_OK;
 }
+template <int NB, int U, int S, int MINB, bool BULK = false>
+static int moc_launch_pipe(const MocParams &p, cudaStream_t st)
+{
+    auto kern = moc_zonal_scan_pipe_kernel<NB, U, S, MINB, BULK>;
+    const size_t smem = (size_t)(kMocThreads / 32) * S * (sizeof(MocStage<U>) + sizeof(int4) + sizeof(uint64_t));
+    if (moc.grid == 0) {
+        int occ = 0;
+        CDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kMocThreads, smem));
+        if (occ < 1) return set_error(CDFGPU_ERR_ARG, "cdfmoc: staged kernel does not fit in shared memory");
+        moc.grid = occ * g.sm_count;
+    }
+    kern<<<moc.grid, kMocThreads, smem, st>>>(p);
+    CDF_CUDA(cudaGetLastError());
+    ++g.launches;
+    return CDFGPU_OK;
+}
 template <int NB>
 static int moc_launch_t(const MocParams &p, cudaStream_t st)
 {
+    if (!p.general) {   // asynchronously staged kernel (moc_kernel_pipe.cuh); non-binary masks keep the literal-chain kernel
+        switch (moc.variant) {
+        // experiments (moc_kernel_pipe.cuh): both feeds are parity-green and slower than the register-staged kernel --
+        // K1 is co-bound by issue slots (a DFMA takes two), and the staging adds instructions
+        case 10: return moc_launch_pipe<NB, 4, 3, 2>(p, st);         // cp.async ring, 16 warps / SM
+        case 23: return moc_launch_pipe<NB, 4, 2, 3, true>(p, st);   // TMA bulk-copy ring, 24 warps / SM
+        }
+    }
     switch (moc.variant) {
     case 1: return moc_launch_v<NB, 4, 4>(p, st);
     case 2: return moc_launch_v<NB, 2, 4>(p, st);
@@ -471,7 +497,7 @@ int cdfmoc_gpu_setup(int nx, int ny, int nz, int nb, const float *e1v, const flo
     REQUIRE(e1v && e3v && ibmask, CDFGPU_ERR_ARG, "cdfmoc_gpu_setup: null pointer");
     cdfmoc_gpu_teardown();
     moc.nx = nx; moc.ny = ny; moc.nz = nz; moc.nb = nb;
-    moc.pitchw = (nx + 6) / 4 + 1;
+    moc.pitchw = ((nx + 6) / 4 + 1 + 3) & ~3;   // rows of the mask planes start on 16-byte boundaries (bulk copies)
     {
         const char *e = getenv("CDFGPU_K1");
         moc.use_tma = e && !strcmp(e, "tma");
@@ -479,7 +505,7 @@ int cdfmoc_gpu_setup(int nx, int ny, int nz, int nb, const float *e1v, const flo
         moc.variant = v ? atoi(v) : 0;
     }
     // rows shorter than ~16 KB are handed out several levels at a time: fewer tickets, fences and column counters
-    moc.chunk = (nx < 4096) ? 2 : 1;   // levels per work unit (sharded tickets make small units affordable)
+    moc.chunk = (nx < 4096) ? 4 : 1;   // levels per work unit (ORCA025: 4 -> 5.49 TB/s, 2 -> 5.39, 1 -> 5.14)
     if (const char *c = getenv("CDFGPU_K1_CHUNK")) moc.chunk = std::max(1, atoi(c));
     const size_t nxy = (size_t)nx * ny;
     CDF_CUDA(cudaMalloc(&moc.d_e1v, nxy * sizeof(float)));

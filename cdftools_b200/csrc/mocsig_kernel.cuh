@@ -52,6 +52,7 @@ struct SigParams {
     const float *__restrict__ gdep;                                    // -isodep: -gdept(k), (nz)
     int *tickets;                                                      // [2]
     int nx, ny, nz, nb, nbins, npat, npat1, pitchw;  // npat incl. the all-zero pattern; npat1 = max(npat-1,1)
+    unsigned npat1_magic;                            // ceil(2^32 / npat1): k / npat1 == umulhi(k, magic) for k < 2^32 / npat1
     int parity;
     int j_first_global, ny_global;
     int eos;  // CDFGPU_EOS_*
@@ -64,6 +65,7 @@ struct SigParams {
     size_t patplane;                              // words per pre-shifted pattern plane = ny * pitchw
     int scrub_ts;                                 // T or S missing value is not zero
     int scrub_v;                                  // V missing value is not zero
+    int use_table;                                // per-warp flush table allocated (hist_flush_table)
 };
 
 // ---- equation of state ----------------------------------------------------------------------------------------
@@ -443,6 +445,83 @@ union SigScratch {
     SigStage st;
     SigQueue q;
 };
+#ifndef CDF_SIG_TABLE_MIN_LANES
+#define CDF_SIG_TABLE_MIN_LANES 4
+#endif
+constexpr int kSigTableMinLanes = CDF_SIG_TABLE_MIN_LANES;
+constexpr int kSigTabRows = 16, kSigTabCols = 16;   // hist_flush_table(): 2 KB per warp, allocated when SigParams::use_table
+
+// This warp's flush table: recomputed from the kernel's shared-memory layout where it is needed (rare path) instead of
+// being carried in a register through the row loop (the kernel sits at the 128-register cap).
+template <bool ISO>
+__device__ __forceinline__ double *sig_tab_ptr(const SigParams &p)
+{
+    extern __shared__ double s_mem[];
+    const size_t nwarps = blockDim.x >> 5;
+    double *comb = s_mem + nwarps * (ISO ? 3 : 1) * ((size_t)p.nbins * p.npat1);
+    SigScratch *stage_all = reinterpret_cast<SigScratch *>(comb + (((size_t)p.nbins * p.nb + 1) & ~(size_t)1));
+    return reinterpret_cast<double *>(stage_all + nwarps) + (size_t)(threadIdx.x >> 5) * (kSigTabRows * kSigTabCols);
+}
+
+// Flush of a dense step in which MANY lanes hold several runs each (fields that change density class from cell to cell).
+// hist_flush() is a chain of dependent warp collectives per round of entries (ballot, match, one shuffle tree per key
+// group): with 8 rounds and only 4 warps per scheduler to hide them, those latencies -- not the EOS -- are what such a
+// step costs.  Here every lane adds its (up to 8) entries of one mask pattern into its own column of a small per-warp
+// table tab[bin - blo][lane mod 16] (the two half-warps take turns on the 16 columns): no two lanes ever touch the same
+// word at the same time, so there is nothing to resolve; then lane r sums row r and adds it to the warp's private
+// histogram.  No atomics, fixed order of additions: bitwise reproducible.  One pass per mask pattern present in the
+// step (usually one or two).  Applies when the bins of the step span fewer than kSigTabRows classes; returns false
+// otherwise and the caller falls back to the round-by-round flush.  The table is left zeroed.
+// Shared memory is not free here: the carve-out steps (... 132, 164, 196, 228 KB) take the space from L1, and L1 bounds
+// the bytes the sweep keeps in flight (sigma0 / 104 bins, smooth fields: 0.515 ms with 113 KB, 0.520 with 145 KB, 0.565
+// with 177 KB), so the host enables the table only while the kernel stays within the 164 KB step (api_mocsig.inc).
+__device__ __forceinline__ bool hist_flush_table(double *hist, double *tab, const int (&kk)[8], const double (&val)[8], int lane,
+                                                 int npat1, unsigned npat1_magic)
+{
+    int bn[8], pt[8];
+    int lo = 0x7fffffff, hi = -1;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int k = max(kk[c], 0);
+        bn[c] = (npat1 == 1) ? k : (int)__umulhi((unsigned)k, npat1_magic);   // k / npat1 (magic = ceil(2^32 / npat1))
+        pt[c] = k - bn[c] * npat1;
+        if (kk[c] >= 0) { lo = min(lo, bn[c]); hi = max(hi, bn[c]); }
+        else pt[c] = -1;
+    }
+    lo = __reduce_min_sync(kFull, lo);
+    hi = __reduce_max_sync(kFull, hi);
+    if (hi < 0) return true;                       // nothing to add
+    if (hi - lo >= kSigTabRows) return false;
+    double *col = tab + (lane & (kSigTabCols - 1)) - (size_t)lo * kSigTabCols;
+    for (int q = 0; q < npat1; ++q) {              // warp-uniform
+        bool mine = false;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) mine |= pt[c] == q;
+        if (!__any_sync(kFull, mine)) continue;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            if ((lane >> 4) == half) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (pt[c] == q) col[bn[c] * kSigTabCols] += val[c];
+            }
+            __syncwarp();
+        }
+        if (lane <= hi - lo) {
+            double *row = tab + lane * kSigTabCols;
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < kSigTabCols; ++i) {
+                const int e = (i + lane) & (kSigTabCols - 1);   // skewed: conflict-free
+                s += row[e];
+                row[e] = 0.0;
+            }
+            hist[(lo + lane) * npat1 + q] += s;
+        }
+        __syncwarp();
+    }
+    return true;
+}
 
 #define FM(a, b, c) fma((a), (b), (c))
 // Fast bins of four cells at once, coefficient-major: sm_100 has no constant-bank operands on DFMA, every coefficient
@@ -751,15 +830,23 @@ __device__ __forceinline__ void sig_dense_compute(const SigParams &p, const SigQ
                 val[c] += val[c - 1];
                 kk[c - 1] = -1;
             }
-        hist_flush(h, kk[7], val[7], lane);
         bool extra = false;
 #pragma unroll
         for (int c = 0; c < 7; ++c) extra |= kk[c] >= 0;
-        if (__any_sync(kFull, extra)) {
-#pragma unroll
-            for (int c = 0; c < 7; ++c)
-                if (__any_sync(kFull, kk[c] >= 0)) hist_flush_few(h, kk[c], val[c], lane);
+        const unsigned xl = __ballot_sync(kFull, extra);
+        if (xl == 0u) {   // one run per lane (smooth fields): a single warp-wide flush
+            hist_flush(h, kk[7], val[7], lane);
+            return;
         }
+        // several lanes with several runs each: the per-lane-column table; a few bin boundaries inside single lanes stay
+        // with the cheap single-lane flushes below
+        if (p.use_table && __popc(xl) >= kSigTableMinLanes &&
+            hist_flush_table(h, sig_tab_ptr<ISO>(p), kk, val, lane, p.npat1, p.npat1_magic))
+            return;
+        hist_flush(h, kk[7], val[7], lane);
+#pragma unroll
+        for (int c = 0; c < 7; ++c)
+            if (__any_sync(kFull, kk[c] >= 0)) hist_flush_few(h, kk[c], val[c], lane);
     };
     pass(hist, [&](int c) { return 0.0 - (double)pr[c]; });
     if (ISO) {   // cdfmocsig.f90:427-428: gdep(jk)*itmask*zarea and itmask*zarea, REAL(4) chains
@@ -843,7 +930,8 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
     double *hist_all = s_mem;                                       // [nwarps][NH][nbins][npat1]
     double *comb = hist_all + (size_t)nwarps * NH * hsize;        // [nbins][nb]
     SigScratch *stage_all = reinterpret_cast<SigScratch *>(comb + (((size_t)p.nbins * p.nb + 1) & ~(size_t)1));  // 16-B aligned
-    unsigned *s_poison = reinterpret_cast<unsigned *>(stage_all + nwarps);  // [nbins]
+    double *tab_all = reinterpret_cast<double *>(stage_all + nwarps);       // [nwarps][kSigTabRows*kSigTabCols] when use_table
+    unsigned *s_poison = reinterpret_cast<unsigned *>(tab_all + (p.use_table ? (size_t)nwarps * kSigTabRows * kSigTabCols : 0));  // [nbins]
     __shared__ int s_ticket[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -851,6 +939,11 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
     const uint64_t pol = make_evict_first_policy();
     double *hist = hist_all + (size_t)warp * NH * hsize;
     SigStage &st = stage_all[warp].st;
+    if (p.use_table) {
+        double *tab = sig_tab_ptr<ISO>(p);
+        for (int t = lane; t < kSigTabRows * kSigTabCols; t += 32) tab[t] = 0.0;
+        __syncwarp();
+    }
     const int NV = (p.nx + 6) >> 2;                 // vectors per row, upper bound over the 4 alignments
     const int wpr = (NV + kSigWinVec - 1) / kSigWinVec;  // windows per (level) row
     const int total = nzm1 * wpr;                   // windows of one latitude row j
