@@ -12,6 +12,7 @@
 #include "mocsig_kernel.cuh"
 #include "moc_decomp.cuh"
 #include "zonal_kernels.cuh"
+#include "transig_kernels.cuh"
 
 namespace cdfgpu {
 
@@ -443,6 +444,7 @@ int cdfgpu_finalize(void)
     cdfmocsig_gpu_teardown();
     cdfzonal_gpu_teardown();
     cdfmhst_gpu_teardown();
+    cdftransig_gpu_teardown();
     cudaStreamDestroy(g.s_compute);
     cudaStreamDestroy(g.s_copy);
     cudaStreamDestroy(g.s_d2h);
@@ -775,3 +777,4 @@ int cdfmoc_gpu_kernel_ms(int slot, float *ms)
 
 #include "api_mocsig.inc"
 #include "api_zonal.inc"
+#include "api_transig.inc"

@@ -64,6 +64,11 @@ SIGNATURES = {
     "cdfmhst_gpu_record": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "cdfmhst_gpu_kernel_ms": (C.c_int, [C.POINTER(C.c_float)]),
     "cdfmhst_gpu_teardown": (C.c_int, []),
+    "cdftransig_gpu_setup": (C.c_int, [C.c_int] * 4 + [C.c_float, C.c_int, C.c_double, C.c_double, C.c_int] + [C.c_void_p] * 5 + [C.c_int]),
+    "cdftransig_gpu_record": (C.c_int, [C.c_void_p] * 6 + [C.c_int]),
+    "cdftransig_gpu_fetch": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cdftransig_gpu_kernel_ms": (C.c_int, [C.POINTER(C.c_float)]),
+    "cdftransig_gpu_teardown": (C.c_int, []),
 }
 
 
@@ -371,3 +376,78 @@ def cdfmhst_kernel_ms() -> float:
 
 def cdfmhst_teardown():
     _chk(load().cdfmhst_gpu_teardown(), "cdfmhst_gpu_teardown")
+
+
+# ---- cdftransig_xy3d (src/cdftransig_xy3d.f90) -------------------------------------------------------------------
+TRANSIG_CODES = {   # -code presets (cdftransig_xy3d.f90:188-197): pref, nbins, ds1min, ds1scal, ds1zoom, ds1scalmin
+    "0": (0.0, 101, 23.0, 0.03, 999.0, 999.0), "1000": (1000.0, 93, 24.2, 0.10, 32.3, 0.05),
+    "1000-acc": (1000.0, 88, 24.5, 0.10, 999.0, 999.0), "2000": (2000.0, 174, 29.0, 0.05, 999.0, 999.0),
+}
+
+
+def transig_bins(nbins, ds1min, ds1scal, ds1zoom=999.0, ds1scalmin=999.0):
+    """Host side of cdftransig_xy3d.f90:213,229-262: bin centres dsigma(nbins), edges dsig_edge(nbins+1), the step -> bin
+    table itab(nsigmax) (1-based bins, 0 = no bin) and the step MIN(ds1scalmin, ds1scal), all in REAL(8)."""
+    ds1scalmin = min(float(ds1scalmin), float(ds1scal))
+    dsigma = np.empty(nbins, np.float64)
+    ijtrans = 0
+    for ji in range(1, nbins + 1):
+        test = ds1min + (ji - 0.5) * ds1scal
+        if test > ds1zoom:
+            if ijtrans == 0:
+                ijtrans = ji
+            dsigma[ji - 1] = ds1zoom + (ji - ijtrans + 0.5) * ds1scalmin
+        else:
+            dsigma[ji - 1] = test
+    edge = np.empty(nbins + 1, np.float64)
+    edge[0] = ds1min
+    for ji in range(2, nbins + 1):
+        edge[ji - 1] = 0.5 * (dsigma[ji - 1] + dsigma[ji - 2])
+    edge[nbins] = edge[nbins - 1] + ds1scalmin
+    x = (edge[nbins] - edge[0]) / ds1scalmin
+    nsigmax = int(np.floor(abs(x) + 0.5)) * (1 if x >= 0 else -1)       # NINT
+    itab = np.zeros(max(nsigmax, 0), np.int32)
+    for ji in range(1, nsigmax + 1):
+        test = ds1min + (ji - 0.5) * ds1scalmin
+        for jj in range(1, nbins + 1):
+            if edge[jj - 1] < test <= edge[jj]:
+                itab[ji - 1] = jj
+    return dsigma, edge, itab, ds1scalmin
+
+
+def cdftransig_setup(e2u, e1v, e3u, e3v, nz, nbins, pref, ds1min, ds1scalmin, itab, lperio=False, teos10=False):
+    """e2u, e1v (ny,nx); e3u, e3v (nz-1,ny,nx) or None (-vvl).  Zeroes the device accumulators."""
+    e2u, e1v = _c32(e2u), _c32(e1v)
+    ny, nx = e1v.shape
+    e3u = _c32(e3u) if e3u is not None else None
+    e3v = _c32(e3v) if e3v is not None else None
+    assert e3u is None or (e3u.shape == (nz - 1, ny, nx) and e3v.shape == (nz - 1, ny, nx))
+    it = np.ascontiguousarray(itab, np.int32)
+    _chk(load().cdftransig_gpu_setup(nx, ny, nz, int(nbins), float(pref), int(teos10), float(ds1min), float(ds1scalmin),
+                                     int(it.size), _ptr(it), _ptr(e2u), _ptr(e1v), _ptr(e3u), _ptr(e3v), int(lperio)),
+         "cdftransig_gpu_setup")
+    return nbins, ny, nx
+
+
+def cdftransig_record(zu, zv, zt, zs, set_masks, e3u_vvl=None, e3v_vvl=None):
+    zu, zv, zt, zs = _c32(zu), _c32(zv), _c32(zt), _c32(zs)
+    eu = _c32(e3u_vvl) if e3u_vvl is not None else None
+    ev = _c32(e3v_vvl) if e3v_vvl is not None else None
+    _chk(load().cdftransig_gpu_record(_ptr(zu), _ptr(zv), _ptr(zt), _ptr(zs), _ptr(eu), _ptr(ev), int(bool(set_masks))),
+         "cdftransig_gpu_record")
+
+
+def cdftransig_fetch(shape):
+    du, dv = np.empty(shape, np.float64), np.empty(shape, np.float64)
+    _chk(load().cdftransig_gpu_fetch(_ptr(du), _ptr(dv)), "cdftransig_gpu_fetch")
+    return du, dv
+
+
+def cdftransig_kernel_ms() -> float:
+    ms = C.c_float()
+    _chk(load().cdftransig_gpu_kernel_ms(C.byref(ms)), "cdftransig_gpu_kernel_ms")
+    return ms.value
+
+
+def cdftransig_teardown():
+    _chk(load().cdftransig_gpu_teardown(), "cdftransig_gpu_teardown")

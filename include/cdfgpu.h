@@ -167,6 +167,25 @@ int cdfmhst_gpu_record(const float *zvt, const float *zvs, int zdim, double *hea
 int cdfmhst_gpu_kernel_ms(float *ms);
 int cdfmhst_gpu_teardown(void);
 
+/* cdftransig_xy3d -- replaces the frame body of src/cdftransig_xy3d.f90:396-461 (kernel K6): the volume transport of
+ * every U / V cell accumulated in density classes, dusigsig / dvsigsig (nx,ny,nbins) REAL(8), resident on the device
+ * across the frames of a run.
+ *   setup : pref = -depref (sigma0 when 0), teos10; ds1min, ds1scalmin = MIN(ds1scalmin, ds1scal) (:213) and the
+ *           step -> bin table itab(nsigmax) the caller builds as at :229-262 (1-based bins; a 0 skips the cell, where the
+ *           reference would index dusigsig(:,:,0)); e2u, e1v (nx,ny); e3u, e3v (nx,ny,nz-1) (NULL with -vvl: then every
+ *           record brings its own); lperio = the E-W periodicity test of :336.  Zeroes the accumulators.
+ *   record: one time frame zu, zv, zt, zs (nx,ny,nz-1), all levels.  set_masks = 1 for the frames of the FIRST tag: the
+ *           reference derives zmasku / zmaskv from those frames only (:410-415) and keeps the last for later tags.
+ *   fetch : the raw sums; the caller divides by nframes and converts to REAL(4) (:466-473). */
+int cdftransig_gpu_setup(int nx, int ny, int nz, int nbins, float pref, int teos10, double ds1min, double ds1scalmin,
+                         int nsigmax, const int32_t *itab, const float *e2u, const float *e1v, const float *e3u,
+                         const float *e3v, int lperio);
+int cdftransig_gpu_record(const float *zu, const float *zv, const float *zt, const float *zs, const float *e3u_vvl,
+                          const float *e3v_vvl, int set_masks);
+int cdftransig_gpu_fetch(double *dusigsig, double *dvsigsig);
+int cdftransig_gpu_kernel_ms(float *ms); /* device time of the last record (both kernels) */
+int cdftransig_gpu_teardown(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -266,3 +266,31 @@ def mhst_record(e1v, e3v, vmask1, zvt, zvs, atl=None, pac=None, ind=None, zdim=F
     lib().oracle_mhst_record(nx, ny, nz, _p(e1v, C.c_float), _p(e3v, C.c_float), _p(vmask1, C.c_float), ptr(a), ptr(p_), ptr(i),
                              _p(zvt, C.c_float), _p(zvs, C.c_float), int(zdim), _p(heat, C.c_double), _p(salt, C.c_double))
     return heat, salt
+
+
+# ---- cdftransig_xy3d --------------------------------------------------------------------
+def transig_bins(nbins, ds1min, ds1scal, ds1zoom=999.0, ds1scalmin=999.0):
+    """-> (dsigma (nbins), dsig_edge (nbins+1), itab (nsigmax) int32 1-based bins, ds1scalmin used).  cdftransig_xy3d.f90:213,229-262."""
+    dsigma, edge = np.empty(nbins, np.float64), np.empty(nbins + 1, np.float64)
+    cap = 1 << 16
+    itab = np.zeros(cap, np.int32)
+    lib().oracle_transig_bins.restype = C.c_int
+    n = lib().oracle_transig_bins(int(nbins), C.c_double(ds1min), C.c_double(ds1scal), C.c_double(ds1zoom), C.c_double(ds1scalmin),
+                                  _p(dsigma, C.c_double), _p(edge, C.c_double), _p(itab, C.c_int32), cap)
+    assert 0 < n <= cap
+    return dsigma, edge, itab[:n].copy(), min(ds1scalmin, ds1scal)
+
+
+def transig_record(e2u, e1v, e3u, e3v, zu, zv, zt, zs, pref, ds1min, ds1scalmin, itab, nbins, dusig, dvsig, masku, maskv,
+                   set_masks=True, lperio=False, teos10=False):
+    """One frame, all levels, accumulated in place into dusig / dvsig (nbins, ny, nx) float64.  cdftransig_xy3d.f90:396-461."""
+    e2u, e1v, e3u, e3v, zu, zv, zt, zs = (_f32(x) for x in (e2u, e1v, e3u, e3v, zu, zv, zt, zs))
+    nzm1, ny, nx = zu.shape
+    it = np.ascontiguousarray(itab, np.int32)
+    assert dusig.dtype == np.float64 and dusig.shape == (nbins, ny, nx) and dusig.flags.c_contiguous
+    assert masku.dtype == np.uint8 and masku.shape == (nzm1, ny, nx)
+    lib().oracle_transig_record(nx, ny, nzm1, int(teos10), C.c_float(pref), int(lperio), C.c_double(ds1min),
+                                C.c_double(ds1scalmin), int(it.size), _p(it, C.c_int32), int(nbins), _p(e2u, C.c_float),
+                                _p(e1v, C.c_float), _p(e3u, C.c_float), _p(e3v, C.c_float), _p(zu, C.c_float),
+                                _p(zv, C.c_float), _p(zt, C.c_float), _p(zs, C.c_float), int(set_masks),
+                                _p(masku, C.c_uint8), _p(maskv, C.c_uint8), _p(dusig, C.c_double), _p(dvsig, C.c_double))

@@ -720,3 +720,104 @@ void oracle_mhst_record(int nx, int ny, int nz, const float *e1v, const float *e
     free(dtrph);
     free(dtrps);
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * cdftransig_xy3d -- src/cdftransig_xy3d.f90.
+ * Bin axis and look-up table (:229-262): dsigma(nbins) bin centres with an optional refined range from ds1zoom,
+ * dsig_edge(nbins+1), and itab(nsigmax) that maps a density counted in steps of ds1scalmin to a bin (1-based; 0 where
+ * no bin claims the step).  Returns nsigmax; itab receives min(nsigmax, itab_cap) entries.
+ * --------------------------------------------------------------------------------------------- */
+int oracle_transig_bins(int nbins, double ds1min, double ds1scal, double ds1zoom, double ds1scalmin_in, double *dsigma,
+                        double *dsig_edge, int *itab, int itab_cap)
+{
+    const double ds1scalmin = ds1scalmin_in < ds1scal ? ds1scalmin_in : ds1scal;   /* :213 MIN(ds1scalmin, ds1scal) */
+    int ijtrans = 0;
+    for (int ji = 1; ji <= nbins; ++ji) {
+        const double dsigtest = ds1min + ((float)ji - 0.5f) * ds1scal;              /* (ji-0.5) is REAL(4), exact */
+        if (dsigtest > ds1zoom) {
+            if (ijtrans == 0) ijtrans = ji;
+            dsigma[ji - 1] = ds1zoom + ((float)(ji - ijtrans) + 0.5f) * ds1scalmin;
+        } else
+            dsigma[ji - 1] = dsigtest;
+    }
+    dsig_edge[0] = ds1min;
+    for (int ji = 2; ji <= nbins; ++ji) dsig_edge[ji - 1] = 0.5f * (dsigma[ji - 1] + dsigma[ji - 2]);
+    dsig_edge[nbins] = dsig_edge[nbins - 1] + ds1scalmin;
+    const int nsigmax = (int)lround((dsig_edge[nbins] - dsig_edge[0]) / ds1scalmin);  /* NINT */
+    for (int ji = 1; ji <= nsigmax && ji <= itab_cap; ++ji) {
+        const double dsigtest = ds1min + ((float)ji - 0.5f) * ds1scalmin;
+        int v = 0;
+        for (int jj = 1; jj <= nbins; ++jj)
+            if (dsigtest > dsig_edge[jj - 1] && dsigtest <= dsig_edge[jj]) v = jj;
+        itab[ji - 1] = v;
+    }
+    return nsigmax;
+}
+
+/* INT() of a REAL(8): truncation toward zero; out of range and NaN give INT_MIN (x86 CVTTSD2SI, what gfortran emits) */
+static inline int f_int_d(double x)
+{
+    if (!(x > -2147483649.0 && x < 2147483648.0)) return (int)0x80000000;
+    return (int)x;
+}
+
+/* One time frame, all levels (:396-453; the reference nests jk outside the frames, the additions into each
+ * dusigsig(i,j,bin) then come in another order -- fp64 rounding only).
+ *   zmasku / zmaskv: 1 where the frame's zu / zv is not 0 -- recomputed only for the frames of the FIRST tag (:410-415);
+ *                    set_masks = 1 stores them (bytes, (nz-1,ny,nx)), 0 uses the stored ones
+ *   dens2d = sigmai(zt, zs, pref)  REAL(8)                                                        (:420-424)
+ *   zdensu(1:nx-1) = REAL(4)(0.5*(dens(i)+dens(i+1))); zdensu(nx) = zdensu(2) if periodic else 0; *zmasku  (:427-435)
+ *   zdensv(:,1:ny-1) likewise in j; row ny is never assigned in the reference (uninitialised): 0 here       (:438-439)
+ *   ijb = clamp(INT((zdens - ds1min)/ds1scalmin)+1, 1, nsigmax); ibin = itab(ijb)                            (:442-453)
+ *   dusigsig(i,j,ibinu) += dble(fl32(e2u * fl32(zu*e3u))) ; dvsigsig likewise with e1v, zv, e3v            (:454-461)
+ * A zero in itab (a step no bin claims) would index dusigsig(:,:,0) in the reference; such cells are skipped here. */
+void oracle_transig_record(int nx, int ny, int nzm1, int teos10, float pref, int lperio, double ds1min, double ds1scalmin,
+                           int nsigmax, const int *itab, int nbins, const float *e2u, const float *e1v, const float *e3u,
+                           const float *e3v, const float *zu, const float *zv, const float *zt, const float *zs,
+                           int set_masks, uint8_t *masku, uint8_t *maskv, double *dusigsig, double *dvsigsig)
+{
+    const size_t nxy = (size_t)nx * ny;
+    double *dens = (double *)malloc(nxy * sizeof(double));
+    float *zdu = (float *)malloc(nxy * sizeof(float)), *zdv = (float *)malloc(nxy * sizeof(float));
+    (void)nbins;
+    for (int k = 0; k < nzm1; ++k) {
+        const size_t o3 = (size_t)k * nxy;
+        oracle_sigmai_dep(nxy, zt + o3, zs + o3, pref, teos10, dens);
+        if (set_masks)
+            for (size_t c = 0; c < nxy; ++c) {
+                masku[o3 + c] = (zu[o3 + c] == 0.0f) ? 0 : 1;
+                maskv[o3 + c] = (zv[o3 + c] == 0.0f) ? 0 : 1;
+            }
+#pragma omp parallel for schedule(static)
+        for (int j = 0; j < ny; ++j) {
+            for (int i = 0; i < nx - 1; ++i) zdu[(size_t)j * nx + i] = (float)(0.5 * (dens[(size_t)j * nx + i] + dens[(size_t)j * nx + i + 1]));
+            zdu[(size_t)j * nx + nx - 1] = (lperio && nx > 2) ? zdu[(size_t)j * nx + 1] : 0.0f;
+            for (int i = 0; i < nx; ++i) {
+                const size_t c = (size_t)j * nx + i;
+                zdu[c] = zdu[c] * (float)masku[o3 + c];
+                zdv[c] = (j < ny - 1) ? (float)(0.5 * (dens[c] + dens[c + nx])) : 0.0f;
+                zdv[c] = zdv[c] * (float)maskv[o3 + c];
+            }
+        }
+#pragma omp parallel for schedule(static)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                const size_t c = (size_t)j * nx + i;
+                int ijb = f_int_d(((double)zdu[c] - ds1min) / ds1scalmin) + 1;
+                ijb = ijb < 1 ? 1 : ijb;
+                ijb = ijb > nsigmax ? nsigmax : ijb;
+                const int bu = itab[ijb - 1];
+                ijb = f_int_d(((double)zdv[c] - ds1min) / ds1scalmin) + 1;
+                ijb = ijb < 1 ? 1 : ijb;
+                ijb = ijb > nsigmax ? nsigmax : ijb;
+                const int bv = itab[ijb - 1];
+                const float tu = zu[o3 + c] * e3u[o3 + c], tv = zv[o3 + c] * e3v[o3 + c];
+                const float pu = e2u[c] * tu, pv = e1v[c] * tv;
+                if (bu >= 1) dusigsig[(size_t)(bu - 1) * nxy + c] = dusigsig[(size_t)(bu - 1) * nxy + c] + (double)pu * 1.0;
+                if (bv >= 1) dvsigsig[(size_t)(bv - 1) * nxy + c] = dvsigsig[(size_t)(bv - 1) * nxy + c] + (double)pv * 1.0;
+            }
+    }
+    free(dens);
+    free(zdu);
+    free(zdv);
+}

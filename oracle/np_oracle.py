@@ -353,3 +353,63 @@ def mhst_record(e1v, e3v, vmask1, zvt, zvs, atl=None, pac=None, ind=None, zdim=F
                 heat[lev, m] = np.cumsum(dtrph[:, sl] * mk[:, sl].astype(f8), axis=1)[:, -1]
                 salt[lev, m] = np.cumsum(dtrps[:, sl] * mk[:, sl].astype(f8), axis=1)[:, -1]
     return heat, salt
+
+
+# ---- cdftransig_xy3d (src/cdftransig_xy3d.f90) -------------------------------------------------------------------
+def transig_bins(nbins, ds1min, ds1scal, ds1zoom=999.0, ds1scalmin=999.0):
+    """Bin centres, edges and the step -> bin look-up table (:213, :229-262).  itab is 1-based, 0 = no bin."""
+    ds1scalmin = min(ds1scalmin, ds1scal)
+    ji = np.arange(1, nbins + 1)
+    test = ds1min + (ji - 0.5) * ds1scal
+    zoom = test > ds1zoom
+    dsigma = test.copy()
+    if zoom.any():
+        ijtrans = int(ji[zoom][0])
+        dsigma[zoom] = ds1zoom + (ji[zoom] - ijtrans + 0.5) * ds1scalmin
+    edge = np.empty(nbins + 1)
+    edge[0] = ds1min
+    edge[1:nbins] = 0.5 * (dsigma[1:] + dsigma[:-1])
+    edge[nbins] = edge[nbins - 1] + ds1scalmin
+    x = (edge[nbins] - edge[0]) / ds1scalmin
+    nsigmax = int(np.floor(abs(x) + 0.5) * np.sign(x))                       # NINT
+    t = ds1min + (np.arange(1, nsigmax + 1) - 0.5) * ds1scalmin
+    itab = np.zeros(nsigmax, np.int32)
+    for jj in range(1, nbins + 1):                                           # the last bin that claims a step wins
+        itab[(t > edge[jj - 1]) & (t <= edge[jj])] = jj
+    return dsigma, edge, itab, ds1scalmin
+
+
+def _int_d(x):
+    """Fortran INT() of REAL(8) with x86 CVTTSD2SI semantics (out of range / NaN -> INT_MIN)."""
+    bad = ~((x > -2147483649.0) & (x < 2147483648.0))
+    r = np.trunc(np.where(bad, 0.0, x)).astype(np.int64)
+    r[bad] = -2147483648
+    return r
+
+
+def transig_record(e2u, e1v, e3u, e3v, zu, zv, zt, zs, pref, ds1min, ds1scalmin, itab, nbins, dusig, dvsig, masku, maskv,
+                   set_masks=True, lperio=False, teos10=False):
+    """One frame, all levels (:396-461), accumulated in place into dusig / dvsig (nbins, ny, nx)."""
+    f32 = np.float32
+    nzm1, ny, nx = zu.shape
+    nsigmax = itab.size
+    jj, ii = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    for k in range(nzm1):
+        dens = sigmai_dep(zt[k], zs[k], f32(pref), teos10)
+        if set_masks:
+            masku[k] = (zu[k] != 0).astype(np.uint8)
+            maskv[k] = (zv[k] != 0).astype(np.uint8)
+        zdu = np.zeros((ny, nx), f32)
+        zdu[:, :-1] = (0.5 * (dens[:, :-1] + dens[:, 1:])).astype(f32)
+        if lperio and nx > 2:
+            zdu[:, -1] = zdu[:, 1]
+        zdu = zdu * masku[k].astype(f32)
+        zdv = np.zeros((ny, nx), f32)
+        zdv[:-1] = (0.5 * (dens[:-1] + dens[1:])).astype(f32)
+        zdv = zdv * maskv[k].astype(f32)
+        for zd, vel, e3, e12, acc in ((zdu, zu[k], e3u[k], e2u, dusig), (zdv, zv[k], e3v[k], e1v, dvsig)):
+            ijb = np.clip(_int_d((zd.astype(np.float64) - ds1min) / ds1scalmin) + 1, 1, nsigmax)
+            b = itab[ijb - 1]
+            p = (e12.astype(f32) * (vel.astype(f32) * e3.astype(f32))).astype(np.float64) * 1.0
+            ok = b >= 1
+            acc[b[ok] - 1, jj[ok], ii[ok]] += p[ok]                          # one (bin, j, i) per cell: no duplicates
