@@ -208,6 +208,35 @@ MODULE cdfgpu
      INTEGER(C_INT) FUNCTION cdfmhst_gpu_teardown() BIND(C, NAME='cdfmhst_gpu_teardown')
        IMPORT :: C_INT
      END FUNCTION cdfmhst_gpu_teardown
+
+     ! ---- cdftransig_xy3d (src/cdftransig_xy3d.f90:396-461): frame body on the GPU, accumulators resident -------------
+     INTEGER(C_INT) FUNCTION cdftransig_gpu_setup(nx, ny, nz, nbins, pref, teos10, ds1min, ds1scalmin, nsigmax, itab, &
+          &                                      e2u, e1v, e3u, e3v, lperio) BIND(C, NAME='cdftransig_gpu_setup')
+       IMPORT :: C_INT, C_FLOAT, C_DOUBLE, C_PTR
+       INTEGER(C_INT), VALUE :: nx, ny, nz, nbins, teos10, nsigmax, lperio
+       REAL(C_FLOAT),  VALUE :: pref                        ! zpref
+       REAL(C_DOUBLE), VALUE :: ds1min, ds1scalmin          ! ds1scalmin = MIN(ds1scalmin, ds1scal) (:213)
+       INTEGER(C_INT), INTENT(in) :: itab(*)                ! (nsigmax), as built at :248-262
+       REAL(C_FLOAT),  INTENT(in) :: e2u(*), e1v(*)         ! (npiglo,npjglo)
+       TYPE(C_PTR), VALUE :: e3u, e3v                       ! C_LOC of (npiglo,npjglo,npk-1), or C_NULL_PTR with -vvl
+     END FUNCTION cdftransig_gpu_setup
+
+     INTEGER(C_INT) FUNCTION cdftransig_gpu_record(zu, zv, zt, zs, e3u_vvl, e3v_vvl, set_masks) &
+          &                                       BIND(C, NAME='cdftransig_gpu_record')
+       IMPORT :: C_INT, C_FLOAT, C_PTR
+       REAL(C_FLOAT), INTENT(in) :: zu(*), zv(*), zt(*), zs(*)   ! one frame, (npiglo,npjglo,npk-1)
+       TYPE(C_PTR), VALUE :: e3u_vvl, e3v_vvl               ! C_NULL_PTR unless -vvl
+       INTEGER(C_INT), VALUE :: set_masks                   ! 1 for the frames of the first tag (jtag == 1, :410)
+     END FUNCTION cdftransig_gpu_record
+
+     INTEGER(C_INT) FUNCTION cdftransig_gpu_fetch(dusigsig, dvsigsig) BIND(C, NAME='cdftransig_gpu_fetch')
+       IMPORT :: C_INT, C_DOUBLE
+       REAL(C_DOUBLE), INTENT(out) :: dusigsig(*), dvsigsig(*)   ! (npiglo,npjglo,nbins) raw sums
+     END FUNCTION cdftransig_gpu_fetch
+
+     INTEGER(C_INT) FUNCTION cdftransig_gpu_teardown() BIND(C, NAME='cdftransig_gpu_teardown')
+       IMPORT :: C_INT
+     END FUNCTION cdftransig_gpu_teardown
   END INTERFACE
 
 CONTAINS
