@@ -12,10 +12,10 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module", autouse=True)
-def _ctx():
-    lib.init(0, 3)
+def _ctx(gpu_lib):
+    """The session-wide library context (conftest.gpu_lib): initialised once, finalised at the end of the session --
+    a module that finalised it on its own would pull the device from under the test modules that follow."""
     yield
-    lib.finalize()
 
 
 def _fields(grid, seed):
