@@ -469,9 +469,9 @@ __device__ __forceinline__ double *sig_tab_ptr(const SigParams &p)
 // step costs.  Here every lane adds its (up to 8) entries of one mask pattern into its own column of a small per-warp
 // table tab[bin - blo][lane mod 16] (the two half-warps take turns on the 16 columns): no two lanes ever touch the same
 // word at the same time, so there is nothing to resolve; then lane r sums row r and adds it to the warp's private
-// histogram.  No atomics, fixed order of additions: bitwise reproducible.  One pass per mask pattern present in the
-// step (usually one or two).  Applies when the bins of the step span fewer than kSigTabRows classes; returns false
-// otherwise and the caller falls back to the round-by-round flush.  The table is left zeroed.
+// histogram.  No atomics, fixed order of additions: bitwise reproducible.  The entries are flushed band by band (a band =
+// kSigTabRows consecutive bins from the lowest bin still pending: a step that holds groups of two windows, i.e. of two
+// levels, has two clusters of bins), one pass per mask pattern present in the band.  The table is left zeroed.
 // Shared memory is not free here: the carve-out steps (... 132, 164, 196, 228 KB) take the space from L1, and L1 bounds
 // the bytes the sweep keeps in flight (sigma0 / 104 bins, smooth fields: 0.515 ms with 113 KB, 0.520 with 145 KB, 0.565
 // with 177 KB), so the host enables the table only while the kernel stays within the 164 KB step (api_mocsig.inc).
@@ -479,46 +479,59 @@ __device__ __forceinline__ bool hist_flush_table(double *hist, double *tab, cons
                                                  int npat1, unsigned npat1_magic)
 {
     int bn[8], pt[8];
-    int lo = 0x7fffffff, hi = -1;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         const int k = max(kk[c], 0);
         bn[c] = (npat1 == 1) ? k : (int)__umulhi((unsigned)k, npat1_magic);   // k / npat1 (magic = ceil(2^32 / npat1))
-        pt[c] = k - bn[c] * npat1;
-        if (kk[c] >= 0) { lo = min(lo, bn[c]); hi = max(hi, bn[c]); }
-        else pt[c] = -1;
+        pt[c] = (kk[c] >= 0) ? k - bn[c] * npat1 : -1;                        // -1: no entry (or already flushed)
     }
-    lo = __reduce_min_sync(kFull, lo);
-    hi = __reduce_max_sync(kFull, hi);
-    if (hi < 0) return true;                       // nothing to add
-    if (hi - lo >= kSigTabRows) return false;
-    double *col = tab + (lane & (kSigTabCols - 1)) - (size_t)lo * kSigTabCols;
-    for (int q = 0; q < npat1; ++q) {              // warp-uniform
-        bool mine = false;
+    double *const mycol = tab + (lane & (kSigTabCols - 1));
+    // A dense step may hold groups of two or more windows, i.e. of different LEVELS (a warp's consecutive windows are
+    // nwarps levels apart): their bins form separate clusters.  Each trip of this loop flushes the band of
+    // kSigTabRows bins that starts at the lowest bin still pending, one pass per mask pattern present in the band.
+    for (;;) {
+        int lo = 0x7fffffff;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) mine |= pt[c] == q;
-        if (!__any_sync(kFull, mine)) continue;
+        for (int c = 0; c < 8; ++c)
+            if (pt[c] >= 0) lo = min(lo, bn[c]);
+        lo = __reduce_min_sync(kFull, lo);
+        if (lo == 0x7fffffff) break;               // warp-uniform: everything is flushed
+        unsigned pm = 0u;
+        int top = lo;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            if ((lane >> 4) == half) {
+        for (int c = 0; c < 8; ++c)
+            if (pt[c] >= 0 && bn[c] - lo < kSigTabRows) { pm |= 1u << pt[c]; top = max(top, bn[c]); }
+        pm = __reduce_or_sync(kFull, pm);
+        const int span = __reduce_max_sync(kFull, top) - lo;
+        double *col = mycol - (size_t)lo * kSigTabCols;
+        while (pm) {                               // warp-uniform
+            const int q = __ffs(pm) - 1;
+            pm &= pm - 1u;
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    if (pt[c] == q) col[bn[c] * kSigTabCols] += val[c];
+            for (int half = 0; half < 2; ++half) {
+                if ((lane >> 4) == half) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (pt[c] == q && bn[c] - lo < kSigTabRows) col[bn[c] * kSigTabCols] += val[c];
+                }
+                __syncwarp();
+            }
+            if (lane <= span) {
+                double *row = tab + lane * kSigTabCols;
+                double s = 0.0;
+#pragma unroll
+                for (int i = 0; i < kSigTabCols; ++i) {
+                    const int e = (i + lane) & (kSigTabCols - 1);   // skewed: conflict-free
+                    s += row[e];
+                    row[e] = 0.0;
+                }
+                hist[(lo + lane) * npat1 + q] += s;
             }
             __syncwarp();
         }
-        if (lane <= hi - lo) {
-            double *row = tab + lane * kSigTabCols;
-            double s = 0.0;
 #pragma unroll
-            for (int i = 0; i < kSigTabCols; ++i) {
-                const int e = (i + lane) & (kSigTabCols - 1);   // skewed: conflict-free
-                s += row[e];
-                row[e] = 0.0;
-            }
-            hist[(lo + lane) * npat1 + q] += s;
-        }
-        __syncwarp();
+        for (int c = 0; c < 8; ++c)
+            if (bn[c] - lo < kSigTabRows) pt[c] = -1;   // this band is done
     }
     return true;
 }
