@@ -25,12 +25,14 @@ def write_mesh(m: synth.Mesh, outdir, with_basins=True, version=2):
     nz, ny, nx = m.e3v_0.shape
     f = _new(out / "mesh_hgr.nc", {"x": nx, "y": ny, "t": None}, version)
     e2v = (m.e1v * np.float32(0.75)).astype(np.float32)   # the synthetic mesh carries no e2v: any positive field will do
-    for name, arr in (("e1v", m.e1v), ("e1u", m.e1u), ("e2v", e2v), ("gphiv", m.gphiv), ("glamv", m.glamv)):
+    e2u = (m.e1u * np.float32(0.9)).astype(np.float32)    # likewise e2u (cdftransig_xy3d)
+    for name, arr in (("e1v", m.e1v), ("e1u", m.e1u), ("e2v", e2v), ("e2u", e2u), ("gphiv", m.gphiv), ("glamv", m.glamv)):
         v = f.createVariable(name, "f", ("t", "y", "x"))
         v[0] = arr
     f.close()
     f = _new(out / "mesh_zgr.nc", {"x": nx, "y": ny, "z": nz, "t": None}, version)
     v = f.createVariable("e3v_0", "f", ("t", "z", "y", "x")); v[0] = m.e3v_0
+    v = f.createVariable("e3u_0", "f", ("t", "z", "y", "x")); v[0] = (m.e3v_0 * np.float32(1.01)).astype(np.float32)
     v = f.createVariable("e3t_0", "f", ("t", "z", "y", "x")); v[0] = m.e3v_0     # presence + rank select 'v3.6'
     for name, arr in (("gdepw_1d", m.gdepw_1d), ("gdept_1d", m.gdept_1d), ("e3t_1d", m.e3t_1d)):
         v = f.createVariable(name, "f", ("t", "z")); v[0] = arr
@@ -46,7 +48,7 @@ def write_mesh(m: synth.Mesh, outdir, with_basins=True, version=2):
         f.close()
 
 
-def write_gridv(m: synth.Mesh, path, nrec, spval=0.0, adversarial=False, eiv=False, version=2):
+def write_gridv(m: synth.Mesh, path, nrec, spval=0.0, adversarial=False, eiv=False, version=2, first=0):
     nz, ny, nx = m.e3v_0.shape
     f = _new(path, {"x": nx, "y": ny, "depthv": nz, "time_counter": None}, version)
     f.start_date = np.int32(20260101)
@@ -64,7 +66,7 @@ def write_gridv(m: synth.Mesh, path, nrec, spval=0.0, adversarial=False, eiv=Fal
     recs = []
     for r in range(nrec):
         tc[r] = 432000.0 * (r + 0.5)
-        rec = synth.make_v_record(m, r, adversarial=adversarial, spval=spval if spval else None)
+        rec = synth.make_v_record(m, first + r, adversarial=adversarial, spval=spval if spval else None)
         v[r] = rec
         recs.append(rec)
         if e is not None:
@@ -73,7 +75,7 @@ def write_gridv(m: synth.Mesh, path, nrec, spval=0.0, adversarial=False, eiv=Fal
     return recs
 
 
-def write_gridt(m: synth.Mesh, path, nrec, spval=0.0, version=2):
+def write_gridt(m: synth.Mesh, path, nrec, spval=0.0, version=2, first=0):
     nz, ny, nx = m.e3v_0.shape
     f = _new(path, {"x": nx, "y": ny, "deptht": nz, "time_counter": None}, version)
     tc = f.createVariable("time_counter", "d", ("time_counter",))
@@ -83,8 +85,8 @@ def write_gridt(m: synth.Mesh, path, nrec, spval=0.0, version=2):
     s.missing_value = np.float32(spval)
     recs = []
     for r in range(nrec):
-        tc[r] = 432000.0 * (r + 0.5)
-        tt, ss = synth.make_ts_record(m, r, spval=spval if spval else None)
+        tc[r] = 432000.0 * (first + r + 0.5)
+        tt, ss = synth.make_ts_record(m, first + r, spval=spval if spval else None)
         t[r] = tt
         s[r] = ss
         recs.append((tt, ss))
@@ -108,5 +110,21 @@ def write_vt(m: synth.Mesh, path, nrec, version=2):
         vt[r] = a
         vs[r] = b
         recs.append((a, b))
+    f.close()
+    return recs
+
+
+def write_gridu(m: synth.Mesh, path, nrec, first=0, version=2):
+    """gridU file: vozocrtx (time_counter, depthu, y, x) f32, zero on land (umask)."""
+    nz, ny, nx = m.e3v_0.shape
+    f = _new(path, {"x": nx, "y": ny, "depthu": nz, "time_counter": None}, version)
+    tc = f.createVariable("time_counter", "d", ("time_counter",))
+    u = f.createVariable("vozocrtx", "f", ("time_counter", "depthu", "y", "x"))
+    recs = []
+    for r in range(nrec):
+        tc[r] = 432000.0 * (first + r + 0.5)
+        rec = (synth.make_v_record(m, 500 + first + r) * m.umask).astype(np.float32)
+        u[r] = rec
+        recs.append(rec)
     f.close()
     return recs

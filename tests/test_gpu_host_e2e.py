@@ -272,3 +272,43 @@ def test_cdfzonalmean_cli_max(tools, oracle_mod, tmp_path):
         assert np.array_equal(f.variables["zomecrty" + sfx + "_min"][0, :, :, 0], zmin[b])
     assert f.variables["zomecrty_atl_max"].long_name.startswith(b"Zonal_Max_")
     f.close()
+
+
+@pytest.mark.parametrize("args,code", [([], (1000.0, 93, 24.2, 0.10, 32.3, 0.05)), (["-code", "0"], (0.0, 101, 23.0, 0.03, 999.0, 999.0)),
+                                       (["-code", "none", "-depref", "2000", "-nbins", "60", "-sigmin", "30", "0.1", "-sigzoom", "34", "0.05"],
+                                        (2000.0, 60, 30.0, 0.1, 34.0, 0.05))])
+def test_cdftransig_cli_matches_oracle(tools, oracle_mod, tmp_path, args, code):
+    """cdftransig_xy3d_gpu on two tags x two frames of DRAKKAR-named files against the oracle (frames of the first tag set
+    the masks, src/cdftransig_xy3d.f90:410-415), output = sums / nframes as REAL(4) on the sigma axis."""
+    m = synth.make_mesh("SMALL")
+    ncfiles.write_mesh(m, tmp_path)
+    frames = []
+    for t, tag in enumerate(("y2026m01", "y2026m02")):
+        us = ncfiles.write_gridu(m, tmp_path / f"SYN-B200_{tag}_gridU.nc", 2, first=2 * t)
+        vs = ncfiles.write_gridv(m, tmp_path / f"SYN-B200_{tag}_gridV.nc", 2, first=2 * t)
+        ts = ncfiles.write_gridt(m, tmp_path / f"SYN-B200_{tag}_gridT.nc", 2, first=2 * t)
+        frames += [(us[r], vs[r], ts[r][0], ts[r][1], t == 0) for r in range(2)]
+    out = _run(tools["cdftransig_xy3d_gpu"], ["-c", "SYN-B200", "-l", "y2026m01", "y2026m02", "-o", "uv.nc"] + args, tmp_path)
+    assert "nbins  = %d" % code[1] in out
+    pref, nb, smin, scal, zoom, smn = code
+    dsig, _, itab, scm = oracle_mod.transig_bins(nb, smin, scal, zoom, smn)
+    du, dv = np.zeros((nb, m.ny, m.nx)), np.zeros((nb, m.ny, m.nx))
+    mu, mv = np.zeros((m.nz - 1, m.ny, m.nx), np.uint8), np.zeros((m.nz - 1, m.ny, m.nx), np.uint8)
+    e2u = (m.e1u * np.float32(0.9)).astype(np.float32)
+    e3u = (m.e3v_0 * np.float32(1.01)).astype(np.float32)
+    lperio = bool(m.glamv[0, 0] == m.glamv[0, m.nx - 2])
+    for zu, zv, zt, zs, first in frames:
+        oracle_mod.transig_record(e2u, m.e1v, e3u[:-1], m.e3v_0[:-1], zu[:-1], zv[:-1], zt[:-1], zs[:-1], pref, smin, scm, itab, nb, du, dv,
+                                  mu, mv, first, lperio)
+    f = netcdf_file(str(tmp_path / "uv.nc"), "r", mmap=False)
+    axis = "sigma_%d" % round(pref / 1000.0)
+    assert f.variables["vouxysig"].shape == (1, nb, m.ny, m.nx) and axis in f.variables
+    assert np.array_equal(f.variables[axis][:], dsig.astype(np.float32))
+    assert f.variables["vouxysig"].units == b"m3/s" and f.variables["vovxysig"].iweight == 4
+    assert np.isclose(f.variables["time_counter"][0], np.mean([432000.0 * (r + 0.5) for r in range(4)]))
+    for name, ref in (("vouxysig", du), ("vovxysig", dv)):
+        got = f.variables[name][0]
+        want = (ref / 4.0).astype(np.float32)
+        assert np.array_equal(got != 0, want != 0), name
+        assert np.allclose(got, want, rtol=2e-7, atol=1e-6), (name, np.abs(got - want).max())
+    f.close()
