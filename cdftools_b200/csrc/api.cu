@@ -9,6 +9,7 @@
 #include "moc_kernel.cuh"
 #include "moc_kernel_tma.cuh"
 #include "moc_kernel_pipe.cuh"
+#include "moc_kernel_class.cuh"
 #include "mocsig_kernel.cuh"
 #include "moc_decomp.cuh"
 #include "zonal_kernels.cuh"
@@ -157,6 +158,13 @@ struct MocPlan {
     int grid = 0;
     size_t smem = 0;
     int variant = 0;       // register-staged kernel: unroll / occupancy variant ($CDFGPU_K1_VARIANT, experiments)
+    // class-run kernel (moc_kernel_class.cuh): 0/1 masks with <= 8 distinct non-zero mask tuples
+    bool use_class = false;
+    int k1_nclass = 0, segpitch = 0, class_grid = 0;
+    uint32_t *d_classw = nullptr;
+    uint8_t *d_segtab = nullptr;
+    std::vector<uint8_t> h_cls;   // class of every (j,i), kept for -vvl rebuilds of the segment table
+    std::vector<float> h_e1v;     // e1v, likewise
     bool use_tma = false;  // $CDFGPU_K1=tma selects the TMA-fed class-sum kernel
     // TMA path (0/1 masks, <= 8 distinct mask tuples, finite area)
     uint8_t *d_classes = nullptr;
@@ -268,6 +276,118 @@ static int moc_launch_t(const MocParams &p, cudaStream_t st)
     return moc_launch_v<NB, 4, 3>(p, st);
 }
 
+
+// Class tables of the class-run kernel (moc_kernel_class.cuh).  cls(j,i) = index of the distinct mask tuple (0 = no
+// basin); a cell is transparent when fl32(e1v*e3m) is zero at every level.  Segment g of alignment s covers the vectors
+// [32g, 32g+32) of the flat 16-byte grid, i.e. the cells [128g - s, 128g - s + 128); positions of existing vectors that
+// fall outside the row count as non-transparent cells of class 0 (their products must not be added).
+static int moc_build_class_tables(const float *e1v, const float *e3m)
+{
+    const int nx = moc.nx, ny = moc.ny, nzm1 = moc.nz - 1;
+    const size_t nxy = (size_t)nx * ny;
+    std::vector<uint8_t> transp(nxy, 1);
+    for (int k = 0; k < nzm1; ++k)
+        for (size_t c = 0; c < nxy; ++c)
+            if (transp[c]) { const float a = e1v[c] * e3m[(size_t)k * nxy + c]; if (!(a == 0.0f)) transp[c] = 0; }
+    const int nvec_max = (nx + 6) >> 2;
+    const int nseg = (nvec_max + 31) / 32;
+    moc.segpitch = ((nseg + 3) / 4) * 4 + 4;   // + one word: the kernel fetches the segment bytes one trip ahead
+    std::vector<uint8_t> seg((size_t)4 * ny * moc.segpitch, (uint8_t)0xFE);
+    for (int s = 0; s < 4; ++s) {
+        const int nvec = (s + nx + 3) >> 2;
+        for (int j = 0; j < ny; ++j) {
+            uint8_t *row = seg.data() + ((size_t)s * ny + j) * moc.segpitch;
+            for (int gsg = 0; gsg < nseg; ++gsg) {
+                int state = 0xFE;
+                for (int pos = 0; pos < 128 && state != 0xFF; ++pos) {
+                    if (32 * gsg + pos / 4 >= nvec) break;
+                    const long i = 128L * gsg - s + pos;
+                    int c;
+                    if (i < 0 || i >= nx) c = 0;
+                    else { if (transp[(size_t)j * nx + i]) continue; c = moc.h_cls[(size_t)j * nx + i]; }
+                    if (state == 0xFE) state = c;
+                    else if (state != c) state = 0xFF;
+                }
+                row[gsg] = (uint8_t)state;
+            }
+        }
+    }
+    if (!moc.d_segtab) CDF_CUDA(cudaMalloc(&moc.d_segtab, seg.size()));
+    CDF_CUDA(cudaMemcpyAsync(moc.d_segtab, seg.data(), seg.size(), cudaMemcpyHostToDevice, g.s_compute));
+    CDF_CUDA(cudaStreamSynchronize(g.s_compute));
+    return CDFGPU_OK;
+}
+
+// classes + one-hot class words; returns with moc.use_class = false when the class formulation does not apply
+static int moc_setup_classes(const float *e1v, const float *e3m, const int16_t *ibmask)
+{
+    const int nx = moc.nx, ny = moc.ny, nb = moc.nb;
+    const size_t nxy = (size_t)nx * ny;
+    moc.use_class = false;
+    {   // experiment, off by default: parity-green but slower than the basin kernel (see moc_kernel_class.cuh)
+        const char *e = getenv("CDFGPU_K1");
+        if (!e || strcmp(e, "class")) return CDFGPU_OK;
+    }
+    uint32_t bits_of[kMocMaxClasses + 1] = {0};
+    int nclass = 1;
+    moc.h_cls.assign(nxy, 0);
+    for (size_t c = 0; c < nxy; ++c) {
+        uint32_t bits = 0;
+        for (int b = 0; b < nb; ++b) if (ibmask[c * nb + b]) bits |= 1u << b;
+        int qn = 0;
+        while (qn < nclass && bits_of[qn] != bits) ++qn;
+        if (qn == nclass) {
+            if (nclass == kMocMaxClasses + 1) return CDFGPU_OK;   // too many distinct mask tuples: basin kernel
+            bits_of[nclass++] = bits;
+        }
+        moc.h_cls[c] = (uint8_t)qn;
+    }
+    if (nclass < 2) return CDFGPU_OK;   // all-zero masks: nothing to gain
+    moc.k1_nclass = nclass - 1;
+    // one-hot class bytes in the 4 pre-shifted word planes (same layout as the basin-bit planes)
+    std::vector<uint32_t> words((size_t)4 * ny * moc.pitchw, 0u);
+    for (int s = 0; s < 4; ++s)
+        for (int j = 0; j < ny; ++j) {
+            uint32_t *row = words.data() + ((size_t)s * ny + j) * moc.pitchw;
+            const uint8_t *crow = moc.h_cls.data() + (size_t)j * nx;
+            for (int w = 0; w < moc.pitchw; ++w) {
+                uint32_t x = 0;
+                for (int c = 0; c < 4; ++c) {
+                    const long i = 4L * w - s + c;
+                    if (i >= 0 && i < nx && crow[i]) x |= (1u << (crow[i] - 1)) << (8 * c);
+                }
+                row[w] = x;
+            }
+        }
+    CDF_CUDA(cudaMalloc(&moc.d_classw, words.size() * sizeof(uint32_t)));
+    CDF_CUDA(cudaMemcpyAsync(moc.d_classw, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, g.s_compute));
+    uint32_t cb[kMocMaxClasses] = {0};
+    for (int qn = 1; qn < nclass; ++qn) cb[qn - 1] = bits_of[qn];
+    CDF_CUDA(cudaMemcpyToSymbolAsync(c_k1_class_bits, cb, sizeof(cb), 0, cudaMemcpyHostToDevice, g.s_compute));
+    CDF_CUDA(cudaStreamSynchronize(g.s_compute));
+    int rc = moc_build_class_tables(e1v, e3m);
+    if (rc) return rc;
+    moc.use_class = true;
+    moc.class_grid = 0;
+    return CDFGPU_OK;
+}
+
+template <int NC>
+static int moc_class_launch_t(const MocClassParams &q, cudaStream_t st)
+{
+    auto kern = moc_zonal_class_kernel<NC, 3>;
+    if (moc.class_grid == 0) {
+        int occ = 0;
+        CDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kMocThreads, 0));
+        if (occ < 1) return set_error(CDFGPU_ERR_ARG, "cdfmoc: class kernel does not fit");
+        moc.class_grid = occ * g.sm_count;
+    }
+    kern<<<moc.class_grid, kMocThreads, 0, st>>>(q);
+    CDF_CUDA(cudaGetLastError());
+    ++g.launches;
+    return CDFGPU_OK;
+}
+
 static int moc_launch(const float *d_zv, double *d_out, Workspace &ws, cudaStream_t st, int noscan = 0)
 {
     if (!noscan && !moc.general && moc.nclass > 0 && moc.use_tma) {  // TMA-fed class-sum kernel
@@ -304,6 +424,20 @@ static int moc_launch(const float *d_zv, double *d_out, Workspace &ws, cudaStrea
     p.general = moc.general;
     p.noscan = noscan;
     ws.parity ^= 1;
+    if (moc.use_class && !moc.general && moc.variant == 0) {   // class-run kernel (moc_kernel_class.cuh)
+        MocClassParams q;
+        q.m = p; q.classw = moc.d_classw; q.segtab = moc.d_segtab; q.segpitch = moc.segpitch; q.nb = moc.nb;
+        switch (moc.k1_nclass) {
+        case 1: return moc_class_launch_t<1>(q, st);
+        case 2: return moc_class_launch_t<2>(q, st);
+        case 3: return moc_class_launch_t<3>(q, st);
+        case 4: return moc_class_launch_t<4>(q, st);
+        case 5: return moc_class_launch_t<5>(q, st);
+        case 6: return moc_class_launch_t<6>(q, st);
+        case 7: return moc_class_launch_t<7>(q, st);
+        case 8: return moc_class_launch_t<8>(q, st);
+        }
+    }
     switch (moc.nb) {
     case 1: return moc_launch_t<1>(p, st);
     case 2: return moc_launch_t<2>(p, st);
@@ -481,7 +615,7 @@ int cdfmoc_gpu_teardown(void)
     if (!moc.ready && !moc.d_area) return CDFGPU_OK;
     if (g.inited) cdfgpu_synchronize();
     cudaFree(moc.d_e1v); cudaFree(moc.d_e3m); cudaFree(moc.d_area); cudaFree(moc.d_maskw);
-    cudaFree(moc.d_ibmask); cudaFree(moc.d_flag); cudaFree(moc.d_classes); cudaFree(moc.d_ext);
+    cudaFree(moc.d_ibmask); cudaFree(moc.d_flag); cudaFree(moc.d_classes); cudaFree(moc.d_ext); cudaFree(moc.d_classw); cudaFree(moc.d_segtab);
     cudaFree(moc.d_e1u); cudaFree(moc.d_zcoef); cudaFree(moc.d_zt); cudaFree(moc.d_zs); cudaFree(moc.d_sig);
     cudaFree(moc.d_hdep); cudaFree(moc.d_zvgeo); cudaFree(moc.d_umask); cudaFree(moc.d_tmask); cudaFree(moc.d_dvbt);
     cudaFree(moc.d_dvgeo); cudaFree(moc.d_sh); cudaFree(moc.d_bt); cudaFree(moc.d_ag); cudaFree(moc.d_btw);
@@ -527,6 +661,8 @@ int cdfmoc_gpu_setup(int nx, int ny, int nz, int nb, const float *e1v, const flo
     CDF_CUDA(cudaMemcpyAsync(moc.d_e1v, e1v, nxy * sizeof(float), cudaMemcpyHostToDevice, g.s_compute));
     CDF_CUDA(cudaMemcpyAsync(moc.d_e3m, e3v, nxy * (size_t)(nz - 1) * sizeof(float), cudaMemcpyHostToDevice, g.s_compute));
     if ((rc = moc_build_area())) return rc;
+    moc.h_e1v.assign(e1v, e1v + nxy);
+    if (binary && (rc = moc_setup_classes(e1v, e3v, ibmask))) return rc;
     moc.smem = (size_t)(kMocThreads / 32) * (nz - 1) * nb * sizeof(double);
     moc.grid = 0;
     // ---- TMA path geometry: tiles of 32*L cells, L = 4 (mod 8) <= 60, ntile tiles per row
@@ -576,7 +712,13 @@ int cdfmoc_gpu_set_e3v(const float *e3v)
     // the area field is read by every kernel in flight: drain first (rare path, once per record with -vvl)
     CDF_CUDA(cudaStreamSynchronize(g.s_compute));
     CDF_CUDA(cudaMemcpyAsync(moc.d_e3m, e3v, (size_t)moc.nx * moc.ny * (moc.nz - 1) * sizeof(float), cudaMemcpyHostToDevice, g.s_compute));
-    return moc_build_area();
+    int rc = moc_build_area();
+    if (rc) return rc;
+    if (moc.use_class) {   // which cells are transparent (zero area at every level) may have changed with e3v
+        moc.h_e1v.resize((size_t)moc.nx * moc.ny);
+        rc = moc_build_class_tables(moc.h_e1v.data(), e3v);
+    }
+    return rc;
 }
 
 int cdfmoc_gpu_submit(int slot, int jt, const float *zv)
