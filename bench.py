@@ -46,6 +46,7 @@ WORKLOADS = {
 }
 DEFAULT_WORKLOAD = "cdfmoc-ORCA025-L75-73rec-5basins"
 METRIC = "MOC cells/s (rec*nx*ny*nz)"
+ALL_CPUS = os.sched_getaffinity(0)   # before any binding
 
 
 def peaks():
@@ -189,6 +190,22 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this rank's threads to the CPUs NVML reports as local to its GPU, BEFORE the pinned host buffers are allocated:
+    with first-touch placement the record buffers then sit on the NUMA node of the GPU's PCIe root, so N ranks stream
+    from N memory controllers instead of all from the node the launcher happened to start on.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        pynvml.nvmlShutdown()
+        return {"cpus": "%d-%d" % (cpus[0], cpus[-1]) if cpus else "", "n": len(cpus)}
+    except Exception as e:   # no NVML / not permitted: run unbound
+        return {"error": str(e)[:80]}
+
+
 # ------------------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -201,6 +218,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- libcdfgpu has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     spec = WORKLOADS[args.workload]
@@ -367,7 +385,8 @@ def run_ours(args):
     e2e = {"value": cells_step_global * e2e_steps / dt, "unit": "cells/s", "h2d_bytes_per_step": nrec * rec_bytes,
            "d2h_bytes_per_step": nrec * int(np.prod(out_shape)) * 8, "steps": e2e_steps,
            "ms_per_step": dt / e2e_steps * 1e3,
-           "path": "cdf%s_gpu_submit/_fetch, 3 slots, pinned host records (per rank)" % ("mocsig" if sig else "moc")}
+           "path": "cdf%s_gpu_submit/_fetch, 3 slots, pinned host records (per rank)" % ("mocsig" if sig else "moc"),
+           "cpu_affinity_rank0": numa}
 
     # ---- parity spot check of the timed kernel against the oracle (sampled latitude rows of one record)
     parity = None
@@ -412,6 +431,11 @@ def run_ours(args):
     if sig:
         del tmask, tbase, sbase
 
+    if rank == 0 and world == 1:   # the CPU baseline uses every host core, not only the GPU-local ones
+        try:
+            os.sched_setaffinity(0, ALL_CPUS)
+        except Exception:
+            pass
     cb = cpu_baseline(spec, m, ib, e3m) if (rank == 0 and world == 1) else None
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
