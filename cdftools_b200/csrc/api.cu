@@ -139,7 +139,7 @@ static bool pack_masks(int nx, int ny, int nb, const int16_t *ibmask, int pitchw
 // =================================================================================================== cdfmoc
 struct MocPlan {
     bool ready = false;
-    int nx = 0, ny = 0, nz = 0, nb = 0, pitchw = 0, general = 0, chunk = 1;
+    int nx = 0, ny = 0, nz = 0, nb = 0, pitchw = 0, general = 0, chunk = 1, jsplit = 0;
     float *d_e1v = nullptr, *d_e3m = nullptr, *d_area = nullptr;
     uint32_t *d_maskw = nullptr;
     int16_t *d_ibmask = nullptr;
@@ -421,6 +421,7 @@ static int moc_launch(const float *d_zv, double *d_out, Workspace &ws, cudaStrea
     p.nx = moc.nx; p.ny = moc.ny; p.nz = moc.nz; p.pitchw = moc.pitchw;
     p.parity = ws.parity;
     p.chunk = moc.chunk;
+    p.jsplit = moc.jsplit;
     p.general = moc.general;
     p.noscan = noscan;
     ws.parity ^= 1;
@@ -643,6 +644,12 @@ int cdfmoc_gpu_setup(int nx, int ny, int nz, int nb, const float *e1v, const flo
     // rows shorter than ~16 KB are handed out several levels at a time: fewer tickets, fences and column counters
     moc.chunk = (nx < 4096) ? 4 : 1;   // levels per work unit (ORCA025: 4 -> 5.49 TB/s, 2 -> 5.39, 1 -> 5.14)
     if (const char *c = getenv("CDFGPU_K1_CHUNK")) moc.chunk = std::max(1, atoi(c));
+    {   // optional guided hand-out: the last 1/den of the columns one level per ticket (a shorter tail of the launch).
+        // Measured neutral on ORCA025 (0.158-0.164 ms for den = 0, 16, 8, 4, 2): off by default; $CDFGPU_K1_TAIL = den
+        int den = 0;
+        if (const char *c = getenv("CDFGPU_K1_TAIL")) den = atoi(c);
+        moc.jsplit = (moc.chunk > 1 && den > 0) ? ny - ny / den : ny;
+    }
     const size_t nxy = (size_t)nx * ny;
     CDF_CUDA(cudaMalloc(&moc.d_e1v, nxy * sizeof(float)));
     CDF_CUDA(cudaMalloc(&moc.d_e3m, nxy * (size_t)(nz - 1) * sizeof(float)));

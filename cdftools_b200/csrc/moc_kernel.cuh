@@ -34,6 +34,7 @@ struct MocParams {
     int nx, ny, nz, pitchw;
     int parity;                         // launch parity selecting tickets[parity]
     int chunk;                          // consecutive levels of one column handed out per ticket
+    int jsplit;                         // columns j >= jsplit are handed out ONE level per ticket (short tail), see kernel
     int general;                        // 1: masks are not 0/1 (or area not finite) -> literal chain everywhere
     int noscan;                         // 1: leave the raw zonal sums in `out` (-decomp combines before integrating)
 };
@@ -149,8 +150,12 @@ __global__ void __launch_bounds__(kMocThreads, MINB) moc_zonal_scan_kernel(const
     // ticket is therefore sharded over kTicketShards counters in different 128-byte lines; shard c owns the units
     // u = t*kTicketShards + c.  A warp starts on shard (global warp id mod shards) and moves on to the next shard when
     // its own runs dry (work stealing), so all shards drain together and the tail is at most one unit per warp.
+    // Guided hand-out: the columns below jsplit go `chunk` levels at a time (few tickets), the last ones a single level at
+    // a time, so that the tail of the launch -- warps idling while the last units finish -- is one row long, not `chunk`.
     const int chunks_per_col = (nzm1 + p.chunk - 1) / p.chunk;
-    const int nunits = p.ny * chunks_per_col;
+    const int jsplit = min(max(p.jsplit, 0), p.ny);
+    const int nbig = jsplit * chunks_per_col;
+    const int nunits = nbig + (p.ny - jsplit) * nzm1;
     int *tickets = p.tickets + p.parity * (kTicketShards * kTicketStride);
     {   // re-arm the next launch's counters
         int *other = p.tickets + (p.parity ^ 1) * (kTicketShards * kTicketStride);
@@ -179,9 +184,18 @@ __global__ void __launch_bounds__(kMocThreads, MINB) moc_zonal_scan_kernel(const
         }
         int unext = 0;
         if (lane == 0) unext = take(shard);  // request the next unit now; its latency hides behind the rows below
-        const int j = u / chunks_per_col;
-        const int k0 = (u - j * chunks_per_col) * p.chunk;
-        const int k1 = min(k0 + p.chunk, nzm1);
+        int j, k0, k1;
+        if (u < nbig) {
+            j = u / chunks_per_col;
+            k0 = (u - j * chunks_per_col) * p.chunk;
+            k1 = min(k0 + p.chunk, nzm1);
+        } else {
+            const int u2 = u - nbig;
+            const int dj = u2 / nzm1;
+            j = jsplit + dj;
+            k0 = u2 - dj * nzm1;
+            k1 = k0 + 1;
+        }
         for (int k = k0; k < k1; ++k) {
             double acc[NB];
 #pragma unroll
