@@ -31,9 +31,10 @@ struct Ctx {
 static Ctx g;
 
 struct Workspace {  // scheduling counters of one stream-ordered sequence of launches
-    int *d_tickets = nullptr;  // [2]
+    int *d_tickets = nullptr;  // [3] sets of sharded counters (K1: three in rotation; the other kernels use the first two)
     int *d_col = nullptr;      // [ny]
     int parity = 0;
+    int gen3 = 0;              // K1 launch generation mod 3
 };
 
 struct Slot {
@@ -74,11 +75,12 @@ static int swap_record(float *d, size_t n, cudaStream_t st)
 
 static int make_ws(Workspace &w, int ny)
 {
-    CDF_CUDA(cudaMalloc(&w.d_tickets, 2 * kTicketShards * kTicketStride * sizeof(int)));
+    CDF_CUDA(cudaMalloc(&w.d_tickets, 3 * kTicketShards * kTicketStride * sizeof(int)));
     CDF_CUDA(cudaMalloc(&w.d_col, (size_t)ny * sizeof(int)));
-    CDF_CUDA(cudaMemsetAsync(w.d_tickets, 0, 2 * kTicketShards * kTicketStride * sizeof(int), g.s_compute));
+    CDF_CUDA(cudaMemsetAsync(w.d_tickets, 0, 3 * kTicketShards * kTicketStride * sizeof(int), g.s_compute));
     CDF_CUDA(cudaMemsetAsync(w.d_col, 0, (size_t)ny * sizeof(int), g.s_compute));
     w.parity = 0;
+    w.gen3 = 0;
     return CDFGPU_OK;
 }
 static void free_ws(Workspace &w)
@@ -166,6 +168,7 @@ struct MocPlan {
     std::vector<uint8_t> h_cls;   // class of every (j,i), kept for -vvl rebuilds of the segment table
     std::vector<float> h_e1v;     // e1v, likewise
     bool use_tma = false;  // $CDFGPU_K1=tma selects the TMA-fed class-sum kernel
+    bool pdl = true;       // programmatic dependent launch of the default kernel ($CDFGPU_K1_PDL=0 switches it off)
     // TMA path (0/1 masks, <= 8 distinct mask tuples, finite area)
     uint8_t *d_classes = nullptr;
     int nclass = 0, lane_cells = 0, ntile = 0, cpitch = 0, tma_warps = 0, tma_grid = 0, tma_chunk = 1;
@@ -233,7 +236,23 @@ static int moc_launch_v(const MocParams &p, cudaStream_t st)
         if (occ < 1) return set_error(CDFGPU_ERR_ARG, "cdfmoc: kernel does not fit (nz*nb too large for shared memory)");
         moc.grid = occ * g.sm_count;
     }
-    kern<<<moc.grid, kMocThreads, moc.smem, st>>>(p);
+    if (moc.pdl) {   // programmatic dependent launch: consecutive K1 launches of a stream overlap tail and ramp-up
+        MocParams q = p;
+        q.pdl = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)moc.grid);
+        cfg.blockDim = dim3(kMocThreads);
+        cfg.dynamicSmemBytes = moc.smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        CDF_CUDA(cudaLaunchKernelEx(&cfg, kern, q));
+    } else {
+        kern<<<moc.grid, kMocThreads, moc.smem, st>>>(p);
+    }
     CDF_CUDA(cudaGetLastError());
     ++g.launches;
     return CDFGPU_OK;
@@ -419,7 +438,9 @@ static int moc_launch(const float *d_zv, double *d_out, Workspace &ws, cudaStrea
     p.tickets = ws.d_tickets;
     p.col_done = ws.d_col;
     p.nx = moc.nx; p.ny = moc.ny; p.nz = moc.nz; p.pitchw = moc.pitchw;
-    p.parity = ws.parity;
+    p.parity = ws.gen3;
+    ws.gen3 = (ws.gen3 + 1) % 3;
+    p.pdl = 0;
     p.chunk = moc.chunk;
     p.jsplit = moc.jsplit;
     p.general = moc.general;
@@ -640,6 +661,8 @@ int cdfmoc_gpu_setup(int nx, int ny, int nz, int nb, const float *e1v, const flo
         moc.use_tma = e && !strcmp(e, "tma");
         const char *v = getenv("CDFGPU_K1_VARIANT");
         moc.variant = v ? atoi(v) : 0;
+        const char *d = getenv("CDFGPU_K1_PDL");
+        moc.pdl = !(d && atoi(d) == 0);
     }
     // rows shorter than ~16 KB are handed out several levels at a time: fewer tickets, fences and column counters
     moc.chunk = (nx < 4096) ? 4 : 1;   // levels per work unit (ORCA025: 4 -> 5.49 TB/s, 2 -> 5.39, 1 -> 5.14)

@@ -32,7 +32,8 @@ struct MocParams {
     int *tickets;                       // [2][kTicketShards*kTicketStride] unit tickets (ping-pong between launches)
     int *col_done;                      // [ny] rows finished per column j (self-resetting)
     int nx, ny, nz, pitchw;
-    int parity;                         // launch parity selecting tickets[parity]
+    int parity;                         // launch generation mod 3 selecting tickets[parity]; this launch re-arms (parity+1)%3
+    int pdl;                            // launched with programmatic stream serialization: may overlap the previous launch's tail
     int chunk;                          // consecutive levels of one column handed out per ticket
     int jsplit;                         // columns j >= jsplit are handed out ONE level per ticket (short tail), see kernel
     int general;                        // 1: masks are not 0/1 (or area not finite) -> literal chain everywhere
@@ -157,10 +158,30 @@ __global__ void __launch_bounds__(kMocThreads, MINB) moc_zonal_scan_kernel(const
     const int nbig = jsplit * chunks_per_col;
     const int nunits = nbig + (p.ny - jsplit) * nzm1;
     int *tickets = p.tickets + p.parity * (kTicketShards * kTicketStride);
-    {   // re-arm the next launch's counters
-        int *other = p.tickets + (p.parity ^ 1) * (kTicketShards * kTicketStride);
-        if (blockIdx.x == 0 && threadIdx.x < kTicketShards) other[threadIdx.x * kTicketStride] = 0;
+    {   // re-arm the next launch's counters (three sets in rotation: with programmatic dependent launch the next launch
+        // starts while this one drains, and IT re-arms the set after its own -- never the one still in use here)
+        int *other = p.tickets + ((p.parity + 1) % 3) * (kTicketShards * kTicketStride);
+        if (blockIdx.x == 0) {
+            // under PDL the set to re-arm may still be in use two launches back if CTAs of the launch in between retired
+            // without work: block 0 re-arms (and only then releases the next launch) once its predecessor is complete
+            if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+            if (threadIdx.x < kTicketShards) {
+                other[threadIdx.x * kTicketStride] = 0;
+                __threadfence();
+            }
+        }
     }
+    // Programmatic dependent launch: the per-launch fixed cost of this kernel (launch gap, ramp-up, and a tail in which
+    // warps idle while the last units finish) is ~28 us whatever the grid -- 18 % of an ORCA025 record (tools/
+    // k1_fixed_cost.py: t = 28 us + bytes / 6.7 TB/s).  Every CTA releases the next launch of the stream right away, so
+    // that its CTAs fill the SMs as ours retire.  The dependent launch may take tickets, stream its first unit and reduce
+    // it, but it parks the sums in shared memory and executes griddepcontrol.wait (= the previous launch has completed and
+    // its writes are visible) before its first global store -- output slabs and column counters may be shared between
+    // consecutive launches.
+    const bool pdl = p.pdl != 0;
+    if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    bool parked = pdl && blockIdx.x != 0;   // this warp's first unit goes to the stash (block 0 has already waited)
+    double *stash = s_scan + (size_t)warp * nzm1 * NB;
     int shard = (blockIdx.x * (kMocThreads / 32) + warp) % kTicketShards;
     auto take = [&](int sh) {   // lane 0: unit index from shard sh (may be >= nunits when the shard is dry)
         return atomicAdd(tickets + sh * kTicketStride, 1) * kTicketShards + sh;
@@ -175,7 +196,12 @@ __global__ void __launch_bounds__(kMocThreads, MINB) moc_zonal_scan_kernel(const
             // only cause one wasted ticket.
             const int seen = __ldcg(tickets + lane * kTicketStride) * kTicketShards + lane;
             unsigned live = __ballot_sync(kFull, seen < nunits);
-            if (live == 0u) break;
+            if (live == 0u) {
+                // no CTA of a dependent launch retires before its predecessor is complete: the launch after this one can
+                // then never run beside the one before it (the grid fills the device), whatever the amount of work
+                if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+                break;
+            }
             live = (live >> shard) | (shard ? (live << (32 - shard)) : 0u);   // rotate so that bit 0 = current shard
             shard = (shard + __ffs(live) - 1) % kTicketShards;
             if (lane == 0) u = take(shard);
@@ -207,14 +233,31 @@ __global__ void __launch_bounds__(kMocThreads, MINB) moc_zonal_scan_kernel(const
                 bad = __any_sync(kFull, badf != badf);
             }
             if (bad) {
+                if (parked) {   // rare: flush what is parked, then the literal chain stores directly
+                    asm volatile("griddepcontrol.wait;" ::: "memory");
+                    __syncwarp();
+                    for (int kk = k0; kk < k; ++kk)
+                        if (lane < NB) p.out[((size_t)kk * p.ny + j) * NB + lane] = stash[(kk - k0) * NB + lane];
+                    parked = false;
+                }
                 row_general_store<NB>(p, j, k, lane);
             } else {
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
                     const double t = warp_sum(acc[b]);
-                    if (lane == b) p.out[((size_t)k * p.ny + j) * NB + b] = t;
+                    if (lane == b) {
+                        if (parked) stash[(k - k0) * NB + b] = t;
+                        else p.out[((size_t)k * p.ny + j) * NB + b] = t;
+                    }
                 }
             }
+        }
+        if (parked) {   // first unit of this warp under PDL: the previous launch must be complete before we store
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            __syncwarp();
+            for (int kk = k0; kk < k1; ++kk)
+                if (lane < NB) p.out[((size_t)kk * p.ny + j) * NB + lane] = stash[(kk - k0) * NB + lane];
+            parked = false;
         }
         // publish the rows, then count them; the warp that completes column j integrates it vertically.
         // Release on the counting atomic (orders this warp's row stores, made visible to lane 0 by __syncwarp) and

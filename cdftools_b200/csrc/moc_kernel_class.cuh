@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kMocThreads, MINB) moc_zonal_class_kernel(cons
     const int nunits = p.ny * chunks_per_col;
     int *tickets = p.tickets + p.parity * (kTicketShards * kTicketStride);
     {
-        int *other = p.tickets + (p.parity ^ 1) * (kTicketShards * kTicketStride);
+        int *other = p.tickets + ((p.parity + 1) % 3) * (kTicketShards * kTicketStride);
         if (blockIdx.x == 0 && threadIdx.x < kTicketShards) other[threadIdx.x * kTicketStride] = 0;
     }
     int shard = (blockIdx.x * (kMocThreads / 32) + (threadIdx.x >> 5)) % kTicketShards;

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kMocThreads, MINB) moc_zonal_scan_pipe_kernel(
     const int nunits = p.ny * chunks_per_col;
     int *tickets = p.tickets + p.parity * (kTicketShards * kTicketStride);
     {   // re-arm the next launch's counters
-        int *other = p.tickets + (p.parity ^ 1) * (kTicketShards * kTicketStride);
+        int *other = p.tickets + ((p.parity + 1) % 3) * (kTicketShards * kTicketStride);
         if (blockIdx.x == 0 && threadIdx.x < kTicketShards) other[threadIdx.x * kTicketStride] = 0;
     }
     // ---- work units: sharded tickets with stealing, exactly as in moc_zonal_scan_kernel --------------------------
