@@ -50,7 +50,8 @@ struct SigParams {
     double *__restrict__ out;                                          // (ny, nbins, nb)
     double *__restrict__ out_iso;                                      // -isodep: (ny, nbins, nb) mean isopycnal depth
     const float *__restrict__ gdep;                                    // -isodep: -gdept(k), (nz)
-    int *tickets;                                                      // [2]
+    int *tickets;                                                      // [3] row tickets, one per launch generation
+    int pdl;                                                           // launched with programmatic stream serialization
     int nx, ny, nz, nb, nbins, npat, npat1, pitchw;  // npat incl. the all-zero pattern; npat1 = max(npat-1,1)
     unsigned npat1_magic;                            // ceil(2^32 / npat1): k / npat1 == umulhi(k, magic) for k < 2^32 / npat1
     int parity;
@@ -960,8 +961,21 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
     const int NV = (p.nx + 6) >> 2;                 // vectors per row, upper bound over the 4 alignments
     const int wpr = (NV + kSigWinVec - 1) / kSigWinVec;  // windows per (level) row
     const int total = nzm1 * wpr;                   // windows of one latitude row j
+    // Programmatic dependent launch, as in K1 (moc_kernel.cuh): a row takes a CTA ~70 us on ORCA025, so the CTAs of a launch
+    // retire over a window that long while the SMs idle; with PDL the CTAs of the next launch of the stream move in as
+    // they leave.  A dependent CTA works through its first row entirely in shared memory and executes
+    // griddepcontrol.wait before the row's epilogue stores; three ticket generations rotate, block 0 re-arms the next
+    // one (and only then releases its own dependents) once the predecessor is complete, and no CTA retires earlier.
     int *ticket = p.tickets + p.parity;
-    if (blockIdx.x == 0 && tid == 0) p.tickets[p.parity ^ 1] = 0;
+    if (blockIdx.x == 0) {
+        if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (tid == 0) {
+            p.tickets[(p.parity + 1) % 3] = 0;
+            __threadfence();
+        }
+    }
+    if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    bool first_row = p.pdl != 0 && blockIdx.x != 0;
 
     if (tid == 0) s_ticket[0] = atomicAdd(ticket, 1);
     int tsel = 0;
@@ -970,7 +984,10 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
         for (int t = tid; t < p.nbins; t += nthreads) s_poison[t] = 0u;
         __syncthreads();
         const int j = s_ticket[tsel];
-        if (j >= p.ny) break;
+        if (j >= p.ny) {
+            if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+            break;
+        }
         if (tid == 0) s_ticket[tsel ^ 1] = atomicAdd(ticket, 1);  // next row's ticket, latency hidden by this row
         tsel ^= 1;
         const int jg = j + p.j_first_global;
@@ -993,6 +1010,10 @@ __global__ void __launch_bounds__(kSigThreads, 1) mocsig_eos_hist_scan_kernel(co
             }
         }
         __syncthreads();
+        if (first_row) {   // PDL: the predecessor must be complete before this launch stores anything
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            first_row = false;
+        }
         // private histograms -> one (fixed order w = 0..nwarps-1: deterministic), in place in warp 0's copy; then
         // patterns -> basins, /1e6, poison handling
         for (int t = tid; t < NH * hsize; t += nthreads) {
