@@ -331,7 +331,9 @@ def run_ours(args):
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "traffic": None, "kernel": kname, "bytes_per_launch": bytes_launch, "ms_per_launch": ms_launch,
                     "peak_source": peak_src, "frac_of_8TBps_spec": achieved / 8000.0,
-                    "note": "per-GPU figure; at N>1 the launch time includes the overlapped NCCL slab gather"}
+                    "note": "per-GPU figure; at N>1 the launch time includes the overlapped NCCL slab gather",
+                    "peak_kind": "measured device-to-device COPY bandwidth (read + write); a read-only streaming kernel can "
+                                 "exceed it slightly (frac > 1) -- see frac_of_8TBps_spec"}
         if sig:
             roofline["second_bound"] = ("instruction issue / fp64 pipe: ~60 instructions (47 fp64) per contributing cell for the "
                                         "FMA-evaluated EOS with exact fallback, plus the histogram flush; see DESIGN.md")

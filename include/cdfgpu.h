@@ -80,7 +80,11 @@ int cdfgpu_set_input_big_endian(int on);
  * fetch   blocks until the slot's record is done and writes dmoc(nb,ny,nz) in Sv, already integrated from the
  *         bottom (cdfmoc.f90:382-388); dmoc(:,:,nz) = 0.
  * compute_device: same kernel on a record that is already in device memory (d_zv, d_dmoc device pointers,
- *         `stream` a cudaStream_t or NULL for the library's compute stream); asynchronous. */
+ *         `stream` a cudaStream_t or NULL for the library's compute stream); asynchronous.
+ * Consecutive cdfmoc (and cdfmocsig) kernels of one stream are launched with programmatic stream serialization: the
+ * next one may start while the previous one drains, but stores nothing before its predecessor is complete, so stream
+ * order holds for every consumer (copies, events, kernels launched the ordinary way), and two launches may share an
+ * output slab.  $CDFGPU_K1_PDL=0 / $CDFGPU_K2_PDL=0 restore plain launches. */
 int cdfmoc_gpu_setup(int nx, int ny, int nz, int nb, const float *e1v, const float *e3v, const int16_t *ibmask);
 int cdfmoc_gpu_set_e3v(const float *e3v);
 int cdfmoc_gpu_submit(int slot, int jt, const float *zv);
