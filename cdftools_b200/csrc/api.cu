@@ -75,9 +75,9 @@ static int swap_record(float *d, size_t n, cudaStream_t st)
 
 static int make_ws(Workspace &w, int ny)
 {
-    CDF_CUDA(cudaMalloc(&w.d_tickets, 3 * kTicketShards * kTicketStride * sizeof(int)));
+    CDF_CUDA(cudaMalloc(&w.d_tickets, (3 * kTicketShards * kTicketStride + 64) * sizeof(int)));   // + the TMA kernel's own pair
     CDF_CUDA(cudaMalloc(&w.d_col, (size_t)ny * sizeof(int)));
-    CDF_CUDA(cudaMemsetAsync(w.d_tickets, 0, 3 * kTicketShards * kTicketStride * sizeof(int), g.s_compute));
+    CDF_CUDA(cudaMemsetAsync(w.d_tickets, 0, (3 * kTicketShards * kTicketStride + 64) * sizeof(int), g.s_compute));
     CDF_CUDA(cudaMemsetAsync(w.d_col, 0, (size_t)ny * sizeof(int), g.s_compute));
     w.parity = 0;
     w.gen3 = 0;
@@ -409,10 +409,11 @@ static int moc_class_launch_t(const MocClassParams &q, cudaStream_t st)
 
 static int moc_launch(const float *d_zv, double *d_out, Workspace &ws, cudaStream_t st, int noscan = 0)
 {
-    if (!noscan && !moc.general && moc.nclass > 0 && moc.use_tma) {  // TMA-fed class-sum kernel
+    if (!noscan && !moc.general && moc.nclass > 0 && moc.use_tma && !moc.decomp) {  // TMA-fed class-sum kernel (experiment; not with -decomp)
         MocTmaParams t;
         t.zv = d_zv; t.area = moc.d_area; t.classes = moc.d_classes; t.ibmask = moc.d_ibmask; t.out = d_out;
-        t.tickets = ws.d_tickets; t.col_done = ws.d_col;
+        t.tickets = ws.d_tickets + 3 * kTicketShards * kTicketStride;   // its own ticket pair, apart from the three sets of the default kernel
+        t.col_done = ws.d_col;
         t.nx = moc.nx; t.ny = moc.ny; t.nz = moc.nz; t.nclass = moc.nclass;
         t.lane_cells = moc.lane_cells; t.ntile = moc.ntile; t.cpitch = moc.cpitch;
         t.parity = ws.parity; t.chunk = moc.tma_chunk; t.warps = moc.tma_warps;
