@@ -58,3 +58,34 @@ def test_cli_contracts(tools, tmp_path, tool):
 def test_cdfmocsig_needs_three_mandatory_arguments(tools, tmp_path):
     r = subprocess.run([tools["cdfmocsig_gpu"], "-v", "V.nc", "-t", "T.nc"], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 99 and "mandatory arguments missing" in r.stdout
+
+
+def test_cdftransig_cli_contracts(tools, tmp_path):
+    """cdftransig_xy3d_gpu: usage, unknown option / bad code / incomplete '-code none' -> STOP 99
+    (src/cdftransig_xy3d.f90:183,200-204), missing mesh files -> 99, missing DRAKKAR file set -> 97 (modutils.f90:111),
+    and -- with all files in place but no GPU in this container -- the library's own STOP 97."""
+    t = tools["cdftransig_xy3d_gpu"]
+    run = lambda *a: subprocess.run([t, *a], capture_output=True, text=True, cwd=tmp_path)
+    r = run()
+    assert r.returncode == 0 and "usage" in r.stdout
+    r = run("-c", "X", "-l", "t1", "-bogus")
+    assert r.returncode == 99 and "unkown option" in r.stdout          # the reference's own spelling
+    r = run("-c", "X", "-l", "t1", "-code", "3000")
+    assert r.returncode == 99 and "is not available" in r.stdout
+    r = run("-c", "X", "-l", "t1", "-code", "none", "-depref", "2000")
+    assert r.returncode == 99 and "individually" in r.stdout
+    r = run("-c", "X", "-l", "t1")
+    assert r.returncode == 99 and "is missing" in r.stdout              # mesh_zgr.nc / mesh_hgr.nc
+    m = synth.make_mesh("TINY")
+    ncfiles.write_mesh(m, tmp_path)
+    r = run("-c", "X", "-l", "t1")
+    assert r.returncode == 97 and "missing gridV" in r.stdout
+    ncfiles.write_gridu(m, tmp_path / "X_t1_gridU.nc", 1)
+    ncfiles.write_gridv(m, tmp_path / "X_t1_gridV.nc", 1)
+    ncfiles.write_gridt(m, tmp_path / "X_t1_gridT.nc", 1)
+    r = run("-c", "X", "-l", "t1", "-v")
+    import torch
+    if not torch.cuda.is_available():                                    # files parsed, bins printed, then no device
+        assert r.returncode == 97 and "NBINS    : 93" in r.stdout and "nbins  = 93" in r.stdout and "libcdfgpu status" in r.stdout
+    else:
+        assert r.returncode == 0
