@@ -450,7 +450,13 @@ union SigScratch {
 #define CDF_SIG_TABLE_MIN_LANES 4
 #endif
 constexpr int kSigTableMinLanes = CDF_SIG_TABLE_MIN_LANES;
-constexpr int kSigTabRows = 16, kSigTabCols = 16;   // hist_flush_table(): 2 KB per warp, allocated when SigParams::use_table
+#ifndef CDF_SIG_TAB_WIDE
+#define CDF_SIG_TAB_WIDE 1
+#endif
+// hist_flush_table(): 2 KB per warp, allocated when SigParams::use_table.  8 bins x 32 columns: every lane has its own
+// column, one round per band (default; sigma0 ORCA025 white noise 0.64 ms), or with CDF_SIG_TAB_WIDE=0 16 bins x 16 columns,
+// the half-warps taking turns (0.68 ms)
+constexpr int kSigTabRows = CDF_SIG_TAB_WIDE ? 8 : 16, kSigTabCols = CDF_SIG_TAB_WIDE ? 32 : 16;
 
 // This warp's flush table: recomputed from the kernel's shared-memory layout where it is needed (rare path) instead of
 // being carried in a register through the row loop (the kernel sits at the 128-register cap).
@@ -468,8 +474,8 @@ __device__ __forceinline__ double *sig_tab_ptr(const SigParams &p)
 // hist_flush() is a chain of dependent warp collectives per round of entries (ballot, match, one shuffle tree per key
 // group): with 8 rounds and only 4 warps per scheduler to hide them, those latencies -- not the EOS -- are what such a
 // step costs.  Here every lane adds its (up to 8) entries of one mask pattern into its own column of a small per-warp
-// table tab[bin - blo][lane mod 16] (the two half-warps take turns on the 16 columns): no two lanes ever touch the same
-// word at the same time, so there is nothing to resolve; then lane r sums row r and adds it to the warp's private
+// table tab[bin - blo][lane]: no two lanes ever touch the same
+// word, so there is nothing to resolve; then lane r sums row r and adds it to the warp's private
 // histogram.  No atomics, fixed order of additions: bitwise reproducible.  The entries are flushed band by band (a band =
 // kSigTabRows consecutive bins from the lowest bin still pending: a step that holds groups of two windows, i.e. of two
 // levels, has two clusters of bins), one pass per mask pattern present in the band.  The table is left zeroed.
@@ -508,6 +514,29 @@ __device__ __forceinline__ bool hist_flush_table(double *hist, double *tab, cons
         while (pm) {                               // warp-uniform
             const int q = __ffs(pm) - 1;
             pm &= pm - 1u;
+#if CDF_SIG_TAB_WIDE
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (pt[c] == q && bn[c] - lo < kSigTabRows) col[bn[c] * kSigTabCols] += val[c];
+            __syncwarp();
+            {   // four lanes per row, 8 columns each
+                const int r = lane >> 2, qtr = lane & 3;
+                double s = 0.0;
+                if (r <= span) {
+                    double *row = tab + r * kSigTabCols + qtr * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int e = (i + r) & 7;
+                        s += row[e];
+                        row[e] = 0.0;
+                    }
+                }
+                s += __shfl_xor_sync(kFull, s, 1);
+                s += __shfl_xor_sync(kFull, s, 2);
+                if (qtr == 0 && r <= span) hist[(lo + r) * npat1 + q] += s;
+            }
+            __syncwarp();
+#else
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 if ((lane >> 4) == half) {
@@ -529,6 +558,7 @@ __device__ __forceinline__ bool hist_flush_table(double *hist, double *tab, cons
                 hist[(lo + lane) * npat1 + q] += s;
             }
             __syncwarp();
+#endif
         }
 #pragma unroll
         for (int c = 0; c < 8; ++c)
