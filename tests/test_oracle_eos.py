@@ -1,5 +1,6 @@
 """Pins the oracle's EOS on the only known-answer values the reference holds (comments in src/eos.f90)."""
 import numpy as np
+import pytest
 
 from oracle import np_oracle as npo
 
@@ -60,3 +61,18 @@ def test_sigma0_equals_pref0_and_dlr0_only(oracle_mod):
     tt = t.astype(np.float64) * (1.0 / 40.0)
     ss = np.sqrt(np.abs(s.astype(np.float64) + 20.0) * (1.0 / 40.0))
     assert np.array_equal(full, (npo._poly_k(E, 0, tt, ss) + 0.0) - 1000.0)
+
+
+def test_coefficient_header_matches_the_reference_source(tmp_path):
+    """include/cdf_eos_coeffs.h is DATA extracted from the reference (tools/gen_eos_coeffs.py, src/eos.f90:214-279,
+    408-466).  Where the reference tree is present (the build container) the header is regenerated and compared; the
+    GPU box has no /root/reference and skips."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    if not Path("/root/reference/src/eos.f90").exists():
+        pytest.skip("reference tree not present")
+    root = Path(__file__).resolve().parent.parent
+    out = tmp_path / "cdf_eos_coeffs.h"
+    subprocess.run([sys.executable, str(root / "tools" / "gen_eos_coeffs.py"), str(out)], check=True, capture_output=True)
+    assert out.read_text() == (root / "include" / "cdf_eos_coeffs.h").read_text()
