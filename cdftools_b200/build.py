@@ -81,7 +81,7 @@ def build_host(force: bool = False) -> dict:
         exe = bindir / name
         deps = [HOST / src] + hdrs + ([SO] if name != "nc3dump" else [])
         if force or not exe.exists() or any(d.stat().st_mtime > exe.stat().st_mtime for d in deps):
-            cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-ffp-contract=off", *HOST_DEFINES.get(name, []), "-o", str(exe), str(HOST / src)]
+            cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-pthread", "-ffp-contract=off", *HOST_DEFINES.get(name, []), "-o", str(exe), str(HOST / src)]
             if name != "nc3dump":
                 cmd += ["-L" + str(PKG), "-lcdfgpu", "-Wl,-rpath," + str(PKG), "-Wl,-rpath,$ORIGIN/.."]
             r = subprocess.run(cmd, capture_output=True, text=True)
