@@ -4,20 +4,22 @@
 //   psi(b,j,nz) = 0 ; psi(b,j,k) = psi(b,j,k+1) + T(b,j,k)/1.d6 , k = nz-1..1            (cdfmoc.f90:385)
 //
 // Design (HBM-bound streaming reduction, 8 algorithmic bytes per level-cell):
-//   * `area` = fl32(e1v*e3m) is precomputed once at setup and stays resident; the five basin masks are packed
-//     into one byte per (j,i) (bit b = basin b) and kept L2-resident, so a record costs 4 B (V) + 4 B (area).
-//   * One warp owns one (j,k) row at a time; rows are handed out dynamically (j-major, atomic ticket, prefetched
-//     one row ahead) to a persistent grid sized to the SM count.  Loads are 16-byte streaming loads on the
-//     FLAT array (rows of the ORCA grids are only 8-byte aligned, so vectors may straddle row ends): the mask
-//     byte-planes are stored in 4 pre-shifted copies whose out-of-row bytes are zero, which both aligns the
-//     mask words with the float4 lanes and masks off the neighbours' cells for free.
-//   * Per cell: one FMUL (fl32 product, exactly the reference's chain when the mask is 0/1), one F2F to fp64,
-//     and one predicated DADD per basin.  fp64 lane partials -> warp shuffle tree.
+//   * `area` = fl32(e1v*e3m) is precomputed once at setup and stays resident; the basin masks are packed into one byte
+//     per (j,i) (bit b = basin b) and kept L2-resident, so a record costs 4 B (V) + 4 B (area) per cell.
+//   * One warp owns one (j,k) row at a time; work units (`chunk` consecutive levels of one latitude row, j-major) are
+//     handed out dynamically through 32 sharded ticket counters with stealing (a same-address L2 atomic completes only
+//     every ~3.6 ns) to a persistent grid of 3 CTAs per SM; the next ticket is requested one unit ahead.
+//   * Loads are 16-byte streaming loads on the FLAT array (rows of the ORCA grids are only 8-byte aligned, so vectors may
+//     straddle row ends): the mask byte-planes are stored in 4 pre-shifted copies whose out-of-row bytes are zero, which
+//     both aligns the mask words with the float4 lanes and masks off the neighbours' cells for free.
+//   * Per cell: one FMUL (fl32 product, exactly the reference's chain when the mask is 0/1), one F2F to fp64, and per
+//     basin one DFMA whose multiplier (-1.0 / -0.0) is built from the mask bit.  fp64 lane partials -> warp shuffle tree.
 //   * Exactness guard: the fast path equals the reference chain whenever masks are in {0,1} and the products are
 //     finite.  A NaN/Inf anywhere in the row is detected for free (fma(p,0,flag)) and the warp then redoes the
-//     row with the literal multiply chain (row_sums_general), which is also the path for non-binary masks.
+//     row with the literal multiply chain (row_general_store), which is also the path for non-binary masks.
 //   * The raw sums go to the output slab; the warp that completes the last level of a column j performs the
 //     bottom-up recurrence in the reference's sequential order (lanes = basins) -- no second kernel.
+//   * Consecutive launches of a stream overlap (programmatic dependent launch): see the kernel body.
 #pragma once
 #include "common.cuh"
 
