@@ -56,6 +56,42 @@ MODULE cdfgpu
        TYPE(C_PTR), VALUE :: p
      END FUNCTION cdfgpu_pinned_free
 
+     INTEGER(C_INT) FUNCTION cdfgpu_abi_version() BIND(C, NAME='cdfgpu_abi_version')
+       IMPORT :: C_INT
+     END FUNCTION cdfgpu_abi_version
+
+     INTEGER(C_INT) FUNCTION cdfgpu_device_count() BIND(C, NAME='cdfgpu_device_count')
+       IMPORT :: C_INT
+     END FUNCTION cdfgpu_device_count
+
+     ! device time (ms) of the last kernel of a slot / tool, for the timing prints of the host program
+     INTEGER(C_INT) FUNCTION cdfmoc_gpu_kernel_ms(slot, ms) BIND(C, NAME='cdfmoc_gpu_kernel_ms')
+       IMPORT :: C_INT, C_FLOAT
+       INTEGER(C_INT), VALUE :: slot
+       REAL(C_FLOAT), INTENT(out) :: ms
+     END FUNCTION cdfmoc_gpu_kernel_ms
+
+     INTEGER(C_INT) FUNCTION cdfmocsig_gpu_kernel_ms(slot, ms) BIND(C, NAME='cdfmocsig_gpu_kernel_ms')
+       IMPORT :: C_INT, C_FLOAT
+       INTEGER(C_INT), VALUE :: slot
+       REAL(C_FLOAT), INTENT(out) :: ms
+     END FUNCTION cdfmocsig_gpu_kernel_ms
+
+     INTEGER(C_INT) FUNCTION cdfzonal_gpu_kernel_ms(ms) BIND(C, NAME='cdfzonal_gpu_kernel_ms')
+       IMPORT :: C_INT, C_FLOAT
+       REAL(C_FLOAT), INTENT(out) :: ms
+     END FUNCTION cdfzonal_gpu_kernel_ms
+
+     INTEGER(C_INT) FUNCTION cdfmhst_gpu_kernel_ms(ms) BIND(C, NAME='cdfmhst_gpu_kernel_ms')
+       IMPORT :: C_INT, C_FLOAT
+       REAL(C_FLOAT), INTENT(out) :: ms
+     END FUNCTION cdfmhst_gpu_kernel_ms
+
+     INTEGER(C_INT) FUNCTION cdftransig_gpu_kernel_ms(ms) BIND(C, NAME='cdftransig_gpu_kernel_ms')
+       IMPORT :: C_INT, C_FLOAT
+       REAL(C_FLOAT), INTENT(out) :: ms
+     END FUNCTION cdftransig_gpu_kernel_ms
+
      ! records given to *_submit are raw big-endian file bytes: byte swap on the device
      INTEGER(C_INT) FUNCTION cdfgpu_set_input_big_endian(on) BIND(C, NAME='cdfgpu_set_input_big_endian')
        IMPORT :: C_INT

@@ -54,3 +54,18 @@ def test_product_never_imports_the_oracle():
             txt = p.read_text(errors="ignore")
             assert "import oracle" not in txt and "from oracle" not in txt and "cdf_oracle" not in txt \
                 and "libcdforacle" not in txt, p
+
+
+def test_fortran_module_binds_the_host_facing_abi():
+    """cdftools_b200/fortran/cdfgpu_mod.f90 (shipped as source: no Fortran compiler here) names every entry point of
+    include/cdfgpu.h that a Fortran host can use; the exceptions take DEVICE pointers or are C-string helpers."""
+    fortran = (ROOT / "cdftools_b200" / "fortran" / "cdfgpu_mod.f90").read_text()
+    bound = set(re.findall(r"NAME='(\w+)'", fortran))
+    device_side_or_c_only = {"cdfmoc_gpu_compute_device", "cdfmocsig_gpu_compute_device", "cdfmocsig_gpu_bins_device",
+                             "cdfgpu_strerror", "cdfgpu_launch_count"}
+    declared = _declared()
+    assert bound <= declared, bound - declared
+    assert declared - bound == device_side_or_c_only, (declared - bound) ^ device_side_or_c_only
+    # every BIND(C) name is the function's own name (a typo there would only show at link time)
+    for fn, name in re.findall(r"FUNCTION\s+(\w+)\s*\([^)]*\)\s*(?:&\s*\n\s*&\s*)?BIND\(C,\s*NAME='(\w+)'\)", fortran):
+        assert fn == name, (fn, name)
