@@ -10,6 +10,7 @@
 #include "moc_kernel_tma.cuh"
 #include "moc_kernel_pipe.cuh"
 #include "moc_kernel_class.cuh"
+#include "eos_device.cuh"
 #include "mocsig_kernel.cuh"
 #include "moc_decomp.cuh"
 #include "zonal_kernels.cuh"
@@ -27,6 +28,7 @@ struct Ctx {
     cudaStream_t s_compute = nullptr, s_copy = nullptr, s_d2h = nullptr;
     unsigned long long launches = 0;
     bool big_endian_input = false;
+    bool device_inputs_ready = false;   // cdfgpu_set_device_inputs_ready
 };
 static Ctx g;
 
@@ -629,6 +631,12 @@ unsigned long long cdfgpu_launch_count(void) { return g.launches; }
 int cdfgpu_set_input_big_endian(int on)
 {
     g.big_endian_input = on != 0;
+    return CDFGPU_OK;
+}
+
+int cdfgpu_set_device_inputs_ready(int on)
+{
+    g.device_inputs_ready = on != 0;
     return CDFGPU_OK;
 }
 

@@ -9,7 +9,7 @@
 //   dmoc_ag     = dmoc - dmoc_sh - dmoc_bt                                                           (:516)
 #pragma once
 #include "common.cuh"
-#include "mocsig_kernel.cuh"   // exact EOS chain (eos_sigma_exact)
+#include "eos_device.cuh"   // exact EOS chain (eos_sigma_exact)
 
 namespace cdfgpu {
 

@@ -15,7 +15,7 @@
 // HBM-bound: about 80 bytes per level-cell (16 dens write + read, 16 velocities + metrics, 2 masks, 2 scattered RMWs).
 #pragma once
 #include "common.cuh"
-#include "mocsig_kernel.cuh"   // exact EOS chain (eos_sigma_exact)
+#include "eos_device.cuh"   // exact EOS chain (eos_sigma_exact)
 
 namespace cdfgpu {
 

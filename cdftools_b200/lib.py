@@ -33,6 +33,7 @@ SIGNATURES = {
     "cdfgpu_pinned_free": (C.c_int, [C.c_void_p]),
     "cdfgpu_launch_count": (C.c_ulonglong, []),
     "cdfgpu_set_input_big_endian": (C.c_int, [C.c_int]),
+    "cdfgpu_set_device_inputs_ready": (C.c_int, [C.c_int]),
     "cdfmoc_gpu_setup": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cdfmoc_gpu_set_e3v": (C.c_int, [C.c_void_p]),
     "cdfmoc_gpu_submit": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
@@ -53,6 +54,8 @@ SIGNATURES = {
     "cdfmocsig_gpu_fetch_isodep": (C.c_int, [C.c_int, C.c_void_p]),
     "cdfmocsig_gpu_compute_device": (C.c_int, [C.c_void_p] * 7),
     "cdfmocsig_gpu_bins_device": (C.c_int, [C.c_void_p] * 4),
+    "cdfmocsig_gpu_bins_device_stats": (C.c_int, [C.c_void_p] * 3 + [C.POINTER(C.c_ulonglong), C.c_void_p]),
+    "cdfmocsig_gpu_filter_info": (C.c_int, [C.POINTER(C.c_double)]),
     "cdfmocsig_gpu_kernel_ms": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
     "cdfmocsig_gpu_teardown": (C.c_int, []),
     "cdfzonal_gpu_setup": (C.c_int, [C.c_int] * 4 + [C.c_void_p] * 4),
@@ -288,6 +291,26 @@ def cdfmocsig_compute_device(d_zv, d_zt, d_zs, d_dmoc, d_zveiv=None, d_e3v_vvl=N
     _chk(load().cdfmocsig_gpu_compute_device(_ptr(d_zv), _ptr(d_zt), _ptr(d_zs), _ptr(d_zveiv), _ptr(d_e3v_vvl),
                                              _ptr(d_dmoc), C.c_void_p(stream_handle(stream))),
          "cdfmocsig_gpu_compute_device")
+
+
+def set_device_inputs_ready(on: bool = True):
+    """Records handed to *_compute_device on a caller stream are resident and synchronised (see cdfgpu.h)."""
+    _chk(load().cdfgpu_set_device_inputs_ready(1 if on else 0), "cdfgpu_set_device_inputs_ready")
+
+
+def cdfmocsig_bins_device_stats(d_zt, d_zs, d_ibin, stream=None):
+    """Bins of a device-resident record plus (cells, cells past the fp32 tier, cells on the reference chain)."""
+    st = (C.c_ulonglong * 3)()
+    _chk(load().cdfmocsig_gpu_bins_device_stats(_ptr(d_zt), _ptr(d_zs), _ptr(d_ibin), st, C.c_void_p(stream_handle(stream))),
+         "cdfmocsig_gpu_bins_device_stats")
+    return int(st[0]), int(st[1]), int(st[2])
+
+
+def cdfmocsig_filter_info() -> dict:
+    v = (C.c_double * 8)()
+    _chk(load().cdfmocsig_gpu_filter_info(v), "cdfmocsig_gpu_filter_info")
+    return {"tier1": bool(v[0]), "tier2": bool(v[1]), "err32_kgm3": v[2], "margin32_bins": v[3], "margin64_bins": v[4],
+            "chunks_per_row": int(v[5]), "levels_per_chunk": int(v[6]), "resident_ctas": int(v[7])}
 
 
 def cdfmocsig_bins_device(d_zt, d_zs, d_ibin, stream=None):

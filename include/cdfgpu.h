@@ -69,6 +69,13 @@ unsigned long long cdfgpu_launch_count(void);
  * does on the CPU inside NF90_GET_VAR, src/cdfio.F90:1593): the byte swap then runs on the device, fused in front of
  * the record's kernel.  on = 0 (default): host-endian REAL(4) as NF90_GET_VAR returns them. */
 int cdfgpu_set_input_big_endian(int on);
+/* *_compute_device on a CALLER's stream: consecutive K1 / K2 launches overlap (programmatic dependent launch), and a launch
+ * may read its device inputs before its predecessor on that stream has finished.  That is only safe when the inputs were
+ * complete before the predecessor was enqueued (resident records).  on = 0 (default): every launch on a caller stream waits
+ * for its predecessor before its first load (safe when a caller kernel right in front produces the inputs); on = 1: the
+ * caller guarantees resident, synchronised inputs and gets the overlap.  Launches on the library's own streams are ordered
+ * by the library itself. */
+int cdfgpu_set_device_inputs_ready(int on);
 
 /* ---- cdfmoc: depth-space MOC ------------------------------------------------------------------------------
  * setup   replaces the one-time part of src/cdfmoc.f90:306,325-336,343-348:
@@ -137,6 +144,14 @@ int cdfmocsig_gpu_fetch_isodep(int slot, double *depi);
 int cdfmocsig_gpu_compute_device(const float *d_zv, const float *d_zt, const float *d_zs, const float *d_zveiv,
                                  const float *d_e3v_vvl, double *d_dmoc, void *stream);
 int cdfmocsig_gpu_bins_device(const float *d_zt, const float *d_zs, int32_t *d_ibin, void *stream);
+/* The same, plus how the three tiers of the bin function shared the work (host array): stats3[0] = cells evaluated,
+ * [1] = cells the fp32 tier did not accept, [2] = cells that took the reference chain.  Blocks until done. */
+int cdfmocsig_gpu_bins_device_stats(const float *d_zt, const float *d_zs, int32_t *d_ibin, unsigned long long *stats3,
+                                    void *stream);
+/* Diagnostics of the current plan: info8 = { fp32 tier on, fp64-FMA tier on, bound on |sigma_fp32 - sigma_reference| (kg/m3),
+ * fp32 margin (bin units), fp64 margin (bin units), chunks of levels per row, levels per chunk, resident CTAs (0 before
+ * the first launch) }. */
+int cdfmocsig_gpu_filter_info(double *info8);
 int cdfmocsig_gpu_kernel_ms(int slot, float *ms);
 int cdfmocsig_gpu_teardown(void);
 

@@ -7,10 +7,12 @@ import oracle
 grid = sys.argv[1] if len(sys.argv) > 1 else "ORCA025"
 pref = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0
 vscale = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0   # 0: no cell contributes -> times the sweep alone
-m = synth.make_mesh(grid)
+rows = tuple(int(x) for x in os.environ["ROWS"].split(",")) if os.environ.get("ROWS") else None   # e.g. ROWS=1338,1721: a band
+m = synth.make_mesh(grid, rows=rows)
 ib = oracle.basin_masks(*synth.basin_mask_inputs(m))
 nb = ib.shape[2]
 lib.init(0, 3)
+lib.set_device_inputs_ready(True)   # resident, synchronised records: consecutive launches may overlap
 g = torch.Generator(device="cuda"); g.manual_seed(1)
 vm = torch.from_numpy(m.vmask[:-1].astype(np.float32)).cuda()
 recs = [(0.1 * vscale * torch.randn((m.nz - 1, m.ny, m.nx), device="cuda", generator=g)) * vm for _ in range(2)]
@@ -22,9 +24,11 @@ nbins = int(os.environ.get('NBINS', nbins))
 eos = int(os.environ.get('EOS', 0))   # 0 EOS80, 1 TEOS10, 2 neutral density
 if eos == 2:
     nbins, smin, sstp = oracle.default_bins(0.0, True)
-lib.cdfmocsig_setup(m.e1v, m.e3v_0, ib, m.nz, nbins, smin, sstp, pref, eos)
+jg = dict(j_first_global=rows[0], ny_global=synth.GRIDS[grid][1]) if rows else {}
+lib.cdfmocsig_setup(m.e1v, m.e3v_0, ib, m.nz, nbins, smin, sstp, pref, eos, **jg)
 if os.environ.get('ISO'):
     lib.cdfmocsig_set_isodep(m.gdept_1d)
+print(json.dumps({"filter": lib.cdfmocsig_filter_info()}))
 st = torch.cuda.Stream()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 cells = m.nx * m.ny * m.nz
@@ -44,7 +48,9 @@ for noise in (0.0, 0.15):
         e1.record(st)
     st.synchronize()
     ms = e0.elapsed_time(e1) / 8
-    print(json.dumps({"kernel": "K2", "grid": grid, "pref": pref, "nbins": nbins, "eos": eos, "iso": bool(os.environ.get("ISO")), "noise": noise, "ms_per_record": round(ms, 4),
+    ibn = torch.empty(vm.shape, dtype=torch.int32, device="cuda")
+    tiers = lib.cdfmocsig_bins_device_stats(trec[0], srec[0], ibn)
+    print(json.dumps({"kernel": "K2", "tiers_cells_past32_exact": tiers, "past32_frac": tiers[1] / max(tiers[0], 1), "grid": grid, "pref": pref, "nbins": nbins, "eos": eos, "iso": bool(os.environ.get("ISO")), "noise": noise, "ms_per_record": round(ms, 4),
                       "cells_per_s": cells / ms * 1e3, "checksum": float(o2.abs().sum().item())}))
     del trec, srec
 lib.cdfmocsig_teardown()
