@@ -39,10 +39,10 @@
 namespace cdfgpu {
 
 #ifndef CDF_SIG_WARPS
-#define CDF_SIG_WARPS 8
+#define CDF_SIG_WARPS 16   // most warps of a CTA (the host launches 16 x 1 CTA or 8 x 2 CTAs per SM: 128 registers either way)
 #endif
 #ifndef CDF_SIG_MINCTAS
-#define CDF_SIG_MINCTAS 2
+#define CDF_SIG_MINCTAS 1
 #endif
 #ifndef CDF_SIG_TAB_ROWS
 #define CDF_SIG_TAB_ROWS 8
@@ -57,10 +57,13 @@ constexpr int kSigMaxPat = 32;
 constexpr int kSigWinVec = 64;                  // one warp step = 64 float4 vectors = 256 cells, 8 consecutive cells per lane
 constexpr int kSigTabRows = CDF_SIG_TAB_ROWS;   // bins covered by the lane-column table
 constexpr int kSigTabSlack = CDF_SIG_TAB_SLACK; // a new band starts this many bins below the lowest pending bin
+#ifndef CDF_SIG_PREFETCH_VA
+#define CDF_SIG_PREFETCH_VA 1   // V / area of window n+2 in flight during window n (0: only T / S of window n+1)
+#endif
 #ifndef CDF_SIG_SEG_WIN
 #define CDF_SIG_SEG_WIN 6
 #endif
-constexpr int kSigSegWin = CDF_SIG_SEG_WIN;     // windows per segment (consecutive windows of one level row), at most
+constexpr int kSigSegWin = CDF_SIG_SEG_WIN;     // windows per run grabbed by a warp, at most
 static_assert(kSigTabRows == 8 || kSigTabRows == 16, "table reduce is written for 8 or 16 rows");
 
 __constant__ double c_patw[kSigMaxPat][CDFGPU_MAX_BASINS];  // weight of pattern p for basin b (= mask value)
@@ -359,8 +362,7 @@ __device__ __forceinline__ float sig_transport(const SigParams &p, float v, floa
 // Register budget: 16 warps / SM leave 128 registers per thread, and the pipeline keeps V / area of window n+2 and T / S of
 // windows n+1 and n in registers (48); everything else a later stage needs is packed (flags) or re-derived: the fp32
 // transports wait in shared memory (32 B per thread and pipeline slot), the pattern words are re-read (L1 hits).
-constexpr unsigned kSigTwo = 0x100u, kSigValid = 0x200u, kSigPoison = 0x400u, kSigWanted = 0x800u, kSigEdge = 0x1000u,
-                   kSigSegStart = 0x2000u;   // flag bits of SigS1::flags / SigS2::need
+constexpr unsigned kSigTwo = 0x100u, kSigValid = 0x200u, kSigPoison = 0x400u, kSigWanted = 0x800u, kSigEdge = 0x1000u;   // flag bits
 // bit c (0..3) of the result: byte c of a pattern word is a real pattern (neither 0 = no basin nor 255 = excluded column)
 __device__ __forceinline__ unsigned sig_covered(uint32_t pw)
 {
@@ -387,42 +389,57 @@ struct SigS2 {          // transports known (shared memory), T / S loads in flig
     bool live;
 };
 
-// The stream of windows of one warp inside a work unit: SEGMENTS (a level, a run of consecutive windows of its row) are
-// handed out by a shared-memory ticket, so a warp's consecutive windows are neighbours at one depth -- their cells fall
-// into the same few density classes (the table's band holds, a lane's running sum carries over) -- and the warps of a CTA
-// stay balanced whatever the land / ocean geometry.
+// The stream of windows of one warp inside a work unit.  The unit's windows are numbered level by level (w = kk * wpr +
+// win); a warp grabs RUNS of consecutive windows from a shared-memory ticket, so its consecutive windows are neighbours at
+// one depth -- their cells fall into the same few density classes and the table's band holds -- and the runs shrink
+// towards the end of the unit (guided self-scheduling: remaining / (2 * warps), between 1 and kSigSegWin windows), so the
+// warps of a CTA reach the unit's barrier together whatever the land / ocean geometry.
 struct SigStream {
-    uint32_t voff0, pidx0;   // of window 0 of the segment's level row, lane 0
+    uint32_t voff0, pidx0;   // of window 0 of the current level row, lane 0
     int nvec;                // vectors of the level row
-    int win, win_end;        // next window, end of the segment
+    int w, w_end;            // next window, end of the run (unit-wide numbering)
+    int win;                 // next window within its level row
     int k;
-    bool fresh;              // the next window is the first of its segment
 };
 
-__device__ __forceinline__ void sig_next_window(const SigParams &p, SigStream &s, SigS1 &a, int *s_seg, int j, int k0, int nseg_total,
-                                                int nseg, int wps, int wpr, int lane, uint64_t pol)
+__device__ __forceinline__ void sig_row_geometry(const SigParams &p, SigStream &s, int j)
+{
+    const uint32_t r = (uint32_t)s.k * (uint32_t)p.ny + (uint32_t)j;
+    const uint64_t e0 = (uint64_t)r * (uint32_t)p.nx;
+    const uint32_t sh = (uint32_t)e0 & 3u;
+    s.nvec = (int)((sh + (uint32_t)p.nx + 3u) >> 2);
+    s.voff0 = (uint32_t)(e0 >> 2);
+    s.pidx0 = (sh * (uint32_t)p.ny + (uint32_t)j) * (uint32_t)p.pitchw;
+}
+
+__device__ __forceinline__ void sig_next_window(const SigParams &p, SigStream &s, SigS1 &a, int *s_seg, int j, int k0, int total,
+                                                int nwarps, int wpr, int lane, uint64_t pol)
 {
     a.live = true;
-    if (s.win >= s.win_end) {   // warp-uniform: take the next segment
-        int sg = 0;
-        if (lane == 0) sg = atomicAdd(s_seg, 1);
-        sg = __shfl_sync(kFull, sg, 0);
-        if (sg >= nseg_total) {
-            a.live = false;
-            s.win = 0; s.win_end = 0;   // stays exhausted
-        } else {
-            const int kk = sg / nseg, part = sg - kk * nseg;
-            s.k = k0 + kk;
-            s.win = part * wps;
-            s.win_end = min(wpr, s.win + wps);
-            const uint32_t r = (uint32_t)s.k * (uint32_t)p.ny + (uint32_t)j;
-            const uint64_t e0 = (uint64_t)r * (uint32_t)p.nx;
-            const uint32_t sh = (uint32_t)e0 & 3u;
-            s.nvec = (int)((sh + (uint32_t)p.nx + 3u) >> 2);
-            s.voff0 = (uint32_t)(e0 >> 2);
-            s.pidx0 = (sh * (uint32_t)p.ny + (uint32_t)j) * (uint32_t)p.pitchw;
-            s.fresh = true;
+    if (s.w >= s.w_end) {   // warp-uniform: grab the next run of windows
+        int start = 0, n = 0;
+        if (lane == 0) {
+            const int rem = total - *reinterpret_cast<volatile int *>(s_seg);
+            n = max(1, min(kSigSegWin, rem / (2 * nwarps)));
+            start = atomicAdd(s_seg, n);
         }
+        start = __shfl_sync(kFull, start, 0);
+        n = __shfl_sync(kFull, n, 0);
+        if (start >= total) {
+            a.live = false;
+            s.w = 0; s.w_end = 0;   // stays exhausted
+        } else {
+            const int kk = start / wpr;
+            s.w = start;
+            s.w_end = min(total, start + n);
+            s.win = start - kk * wpr;
+            s.k = k0 + kk;
+            sig_row_geometry(p, s, j);
+        }
+    } else if (s.win == wpr) {   // the run continues on the next level row
+        s.win = 0;
+        ++s.k;
+        sig_row_geometry(p, s, j);
     }
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     a.va = z4; a.vb = z4; a.aa = z4; a.ab = z4;
@@ -431,12 +448,12 @@ __device__ __forceinline__ void sig_next_window(const SigParams &p, SigStream &s
         const int v0 = s.win * kSigWinVec + 2 * lane;
         a.voff = s.voff0 + (uint32_t)v0;
         a.pidx = s.pidx0 + (uint32_t)v0;
-        a.flags = ((unsigned)s.k << 16) | (s.fresh ? kSigSegStart : 0u);
-        s.fresh = false;
+        a.flags = (unsigned)s.k << 16;
         if (v0 < s.nvec) a.flags |= kSigValid;
         if (v0 + 1 < s.nvec) a.flags |= kSigTwo;
         if (v0 == 0 || v0 + 2 >= s.nvec) a.flags |= kSigEdge;   // the row's first / last vector: may hold cells of the neighbour rows
         ++s.win;
+        ++s.w;
         if (a.flags & kSigValid) {
             const float4 *pv = reinterpret_cast<const float4 *>(p.zv) + a.voff;
             const float4 *pa = reinterpret_cast<const float4 *>(p.area) + a.voff;
@@ -501,7 +518,7 @@ __device__ __forceinline__ void sig_stage2(const SigParams &p, const SigS1 &a, S
         if (wanted) {
             d.need |= kSigWanted;
             prs[0] = make_float4(pr[0], pr[1], pr[2], pr[3]);
-            prs[kSigThreads] = make_float4(pr[4], pr[5], pr[6], pr[7]);
+            prs[blockDim.x] = make_float4(pr[4], pr[5], pr[6], pr[7]);
         }
     }
     if (__any_sync(kFull, zacc != zacc)) d.need |= kSigPoison;
@@ -617,7 +634,7 @@ __device__ __forceinline__ void sig_stage3(const SigParams &p, const SigS2 &d, c
     float4 qa = z4, qb = z4;
     uint32_t pw0 = 0u, pw1 = 0u;
     if (wanted) {
-        qa = prs[0]; qb = prs[kSigThreads];
+        qa = prs[0]; qb = prs[blockDim.x];
         pw0 = __ldg(p.patw + d.pidx);
         if (d.need & kSigTwo) pw1 = __ldg(p.patw + d.pidx + 1);
     }
@@ -694,14 +711,16 @@ template <bool NEUTRAL, bool ISO>
 __global__ void __launch_bounds__(kSigThreads, kSigMinCtas) mocsig_eos_hist_scan_kernel(const __grid_constant__ SigParams p)
 {
     extern __shared__ double s_mem[];
-    const int nwarps = blockDim.x >> 5, nthreads = blockDim.x;     // <= kSigWarps: fewer when the histograms are large (host)
+    const int nwarps = blockDim.x >> 5, nthreads = blockDim.x;     // <= kSigWarps: chosen by the host
     const int hsize = p.nbins * p.npat1;                            // one private histogram
     constexpr int NH = ISO ? 3 : 1;                                 // histograms per warp: transport [, depth*area, area]
     double *hist_all = s_mem;                                       // [nwarps][NH][nbins][npat1]
     double *tab_all = hist_all + (size_t)nwarps * NH * hsize;       // [nwarps][kSigTabRows][32]
     double *comb = tab_all + (size_t)nwarps * kSigTabRows * 32;     // [nbins][nb]
     unsigned *s_poison = reinterpret_cast<unsigned *>(comb + (size_t)p.nbins * p.nb);   // [nbins]
-    __shared__ float4 s_prs[2][2][kSigThreads];   // fp32 transports of the two windows past stage 2, per thread
+    // fp32 transports of the two windows past stage 2, per thread: [slot][half][thread], 16-byte aligned
+    float4 *s_prs = reinterpret_cast<float4 *>(s_mem + (((size_t)nwarps * (NH * hsize + kSigTabRows * 32) + (size_t)p.nbins * p.nb +
+                                                          (p.nbins + 1) / 2 + 1) & ~(size_t)1));
     __shared__ int s_ticket[2];
     __shared__ int s_last, s_seg;
 
@@ -754,25 +773,30 @@ __global__ void __launch_bounds__(kSigThreads, kSigMinCtas) mocsig_eos_hist_scan
         const bool skip_row = (p.ny_global > 1) && (jg == 0 || jg == p.ny_global - 1);  // jj = 2..npjglo-1 only (:405-407)
 
         if (!skip_row && nk > 0) {
-            // segments of <= kSigSegWin consecutive windows of one level row, handed to the warps by a shared-memory ticket
-            const int nseg = (wpr + kSigSegWin - 1) / kSigSegWin, wps = (wpr + nseg - 1) / nseg;
-            const int nseg_total = nk * nseg;
+            const int total = nk * wpr;   // windows of the unit, handed to the warps in runs by a shared-memory ticket
             SigTabState st;
             st.base = -0x40000000; st.dirty = false;
             SigStream ws;
-            ws.win = 0; ws.win_end = 0; ws.k = 0; ws.nvec = 0; ws.voff0 = 0u; ws.pidx0 = 0u; ws.fresh = false;
+            ws.w = 0; ws.w_end = 0; ws.win = 0; ws.k = 0; ws.nvec = 0; ws.voff0 = 0u; ws.pidx0 = 0u;
             SigS1 a;
             SigS2 x, y;
-            float4 *const prx = &s_prs[0][0][tid], *const pry = &s_prs[1][0][tid];
-            sig_next_window(p, ws, a, &s_seg, j, k0, nseg_total, nseg, wps, wpr, lane, pol);
+            float4 *const prx = s_prs + tid, *const pry = s_prs + 2 * nthreads + tid;
+            sig_next_window(p, ws, a, &s_seg, j, k0, total, nwarps, wpr, lane, pol);
             sig_stage2<ISO>(p, a, x, prx, lane, pol);
-            sig_next_window(p, ws, a, &s_seg, j, k0, nseg_total, nseg, wps, wpr, lane, pol);
+#if CDF_SIG_PREFETCH_VA
+            sig_next_window(p, ws, a, &s_seg, j, k0, total, nwarps, wpr, lane, pol);
+#endif
             // x: window n (T / S in flight, transports in slot `slot`), a: window n+1 (V / area in flight)
             int slot = 0;
 #pragma unroll 1
             while (x.live) {
+#if CDF_SIG_PREFETCH_VA
                 sig_stage2<ISO>(p, a, y, slot ? prx : pry, lane, pol);
-                sig_next_window(p, ws, a, &s_seg, j, k0, nseg_total, nseg, wps, wpr, lane, pol);
+                sig_next_window(p, ws, a, &s_seg, j, k0, total, nwarps, wpr, lane, pol);
+#else
+                sig_next_window(p, ws, a, &s_seg, j, k0, total, nwarps, wpr, lane, pol);
+                sig_stage2<ISO>(p, a, y, slot ? prx : pry, lane, pol);
+#endif
                 sig_stage3<NEUTRAL, ISO>(p, x, slot ? pry : prx, hist, tab, st, s_poison, hsize, lane, pol);
                 x = y;
                 slot ^= 1;
