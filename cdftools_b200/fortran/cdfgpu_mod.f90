@@ -98,6 +98,12 @@ MODULE cdfgpu
        INTEGER(C_INT), VALUE :: on
      END FUNCTION cdfgpu_set_input_big_endian
 
+     ! diagnostics of the current cdfmocsig plan (tiers of the bin function, work units): info(8), see cdfgpu.h
+     INTEGER(C_INT) FUNCTION cdfmocsig_gpu_filter_info(info8) BIND(C, NAME='cdfmocsig_gpu_filter_info')
+       IMPORT :: C_INT, C_DOUBLE
+       REAL(C_DOUBLE), INTENT(out) :: info8(8)
+     END FUNCTION cdfmocsig_gpu_filter_info
+
      ! ---- cdfmoc ------------------------------------------------------------
      INTEGER(C_INT) FUNCTION cdfmoc_gpu_setup(nx, ny, nz, nb, e1v, e3v, ibmask) BIND(C, NAME='cdfmoc_gpu_setup')
        IMPORT :: C_INT, C_FLOAT, C_INT16_T
