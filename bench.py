@@ -100,11 +100,10 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ case construction
 def build_case(spec, rows=None):
-    from cdftools_b200 import synth
-    import oracle  # checker only: assembles masks exactly as the reference does and provides the CPU baseline
+    from cdftools_b200 import synth   # (the oracle is not needed to build inputs: it is imported by the checker legs only)
     m = synth.make_mesh(spec["grid"], rows=rows)
-    ib = oracle.basin_masks(*synth.basin_mask_inputs(m))
-    e3m = oracle.mask_e3v(m.e3v_0, m.vmask.astype(np.float32)) if spec["kernel"] == "moc" else None
+    ib = synth.setup_masks(m)
+    e3m = synth.setup_e3v_masked(m) if spec["kernel"] == "moc" else None
     return m, ib, e3m
 
 
@@ -135,9 +134,20 @@ def host_records(spec, m, n):
     return recs
 
 
+def use_all_host_cores():
+    """The CPU arms use every host core: undo the GPU-local CPU binding and the OMP_NUM_THREADS=1 that torchrun exports."""
+    import oracle
+    try:
+        os.sched_setaffinity(0, ALL_CPUS)
+    except Exception:
+        pass
+    oracle.set_num_threads(len(ALL_CPUS))
+    return oracle.num_threads()
+
+
 def cpu_baseline(spec, m, ib, e3m, budget_s=15.0, max_rec=6):
     """Oracle port timed on the host cores (OpenMP over jj, as src/cdfmoc.f90:369 / cdfmocsig.f90:413)."""
-    import oracle
+    cores = use_all_host_cores()
     arrs = host_records(spec, m, 1)[0]
     t0 = time.perf_counter()
     oracle_record(spec, m, ib, e3m, arrs)
@@ -151,9 +161,9 @@ def cpu_baseline(spec, m, ib, e3m, budget_s=15.0, max_rec=6):
     what = ("C restatement of src/cdfmoc.f90:352-388" if spec["kernel"] == "moc" else
             "C restatement of src/cdfmocsig.f90:366-475 + eos.f90:842-882, direct-scatter form (the reference's dense "
             "nb*nbins*nx pass per (j,k), cdfmocsig.f90:435-442, is several times slower)")
-    return {"value": cells / dt, "unit": "cells/s", "cores": oracle.num_threads(), "kind": "port",
+    return {"value": cells / dt, "unit": "cells/s", "cores": cores, "kind": "port",
             "sample": f"{n} record(s) of the same grid, compute only (arrays in RAM), {dt * 1e3:.1f} ms/record; "
-                      f"{what}, gcc -O3 -ffp-contract=off -fopenmp"}
+                      f"{what}, gcc -O3 -ffp-contract=off -fopenmp, {cores} OpenMP threads"}
 
 
 def run_reference(args):
@@ -161,7 +171,7 @@ def run_reference(args):
         return
     spec = WORKLOADS[args.workload]
     m, ib, e3m = build_case(spec)
-    import oracle
+    cores = use_all_host_cores()   # explicitly: under torchrun OMP_NUM_THREADS=1 would leave the port single-threaded
     cells = m.nx * m.ny * m.nz
     arrs = host_records(spec, m, 1)[0]
     t0 = time.perf_counter()
@@ -175,16 +185,16 @@ def run_reference(args):
         oracle_record(spec, m, ib, e3m, arrs)
     dt = time.perf_counter() - t0
     val = cells * per_step * args.steps / dt
-    cores = oracle.num_threads()
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "cells/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak" if spec["shard"] == "time" else "strong", "vs_baseline": None,
             "dtype": "f32 products, f64 sums", "data": "synthetic",
             "config": {"workload": args.workload, "grid": spec["grid"], "records_per_step": per_step,
+                       "host_cpus": len(ALL_CPUS), "omp_threads": cores,
                        "note": "host CPU only; gfortran/netcdf absent so the reference binary cannot be built: this is "
                                "the C restatement of the reference loops with the reference's OpenMP directives"},
             "cpu_baseline": {"value": val, "unit": "cells/s", "cores": cores, "kind": "port",
-                             "sample": f"{per_step} record(s) per step x {args.steps} steps, compute only"},
+                             "sample": f"{per_step} record(s) per step x {args.steps} steps, compute only, {cores} OpenMP threads"},
             "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -207,37 +217,74 @@ def bind_to_gpu_numa_node(index: int):
 
 
 # ------------------------------------------------------------------------------------------------------- our arm
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from cdftools_b200 import lib, shard
+class Ctx:
+    """What every measurement of this process shares."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- libcdfgpu has no CPU fallback")
-    torch.cuda.set_device(local)
-    numa = bind_to_gpu_numa_node(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    spec = WORKLOADS[args.workload]
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from cdftools_b200 import lib, shard
+        self.torch, self.dist, self.lib, self.shard, self.args = torch, dist, lib, shard, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- libcdfgpu has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.numa = bind_to_gpu_numa_node(self.local)
+        if self.world > 1:
+            # the slab gather is small next to the kernels' traffic: a few NCCL channels keep it off the SMs the persistent
+            # kernels occupy (each channel is a resident CTA)
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", str(args.nccl_channels))
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        lib.init(self.local, 3)
+        lib.set_device_inputs_ready(True)   # records are resident and synchronised before the timed launches
+        self.t_start = time.perf_counter()
+        self.hbm_peak, self.peak_src = peaks()
+
+    def elapsed(self):
+        return time.perf_counter() - self.t_start
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+
+def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=True, do_smooth=True, do_cpu=False,
+            clocks=None):
+    """One workload on this process' GPU (all ranks call it together): kernel phase with the NCCL slab gather, roofline,
+    optional end-to-end pipeline, parity spot check against the oracle on rank 0.  Returns the JSON-able record (rank 0
+    holds the meaningful one)."""
+    torch, dist, lib, shard, args = cx.torch, cx.dist, cx.lib, cx.shard, cx.args
+    rank, world = cx.rank, cx.world
+    spec = WORKLOADS[workload]
     sig = spec["kernel"] == "sig"
     band = spec["shard"] == "band"
     from cdftools_b200 import synth
     nxg, nyg, nzg = synth.GRIDS[spec["grid"]]
-    j0, j1 = shard.band_plan(nyg, world)[rank] if band else (0, nyg)
+    bands = shard.band_plan(nyg, world)
+    j0, j1 = bands[rank] if band else (0, nyg)
     m, ib, e3m = build_case(spec, rows=(j0, j1) if band else None)
     nx, ny, nz, nb = m.nx, m.ny, m.nz, ib.shape[2]
-    nrec = spec["nrec"]
+    nrec = spec["nrec"] if nrec is None else min(nrec, spec["nrec"])
     cells_rec_local = nx * ny * nz
     cells_step_global = (nrec * nxg * nyg * nzg) if band else (world * nrec * cells_rec_local)
-    lib.init(local, 3)
     if sig:
         smin, sstp, nbins = spec["bins"]
         lib.cdfmocsig_setup(m.e1v, m.e3v_0, ib, nz, nbins, smin, sstp, spec["pref"], lib.EOS80,
                             j_first_global=j0, ny_global=nyg)
-        out_shape = (ny, nbins, nb)
+        mxrows = max(b1 - b0 for b0, b1 in bands) if band else ny
+        out_shape = (mxrows, nbins, nb)          # a band's slab is padded to the largest band: equal slabs for the gather
         bytes_launch = (nz - 1) * ny * nx * 16 + ny * nx * 1 + nb * nbins * ny * 8
         kname = "mocsig_eos_hist_scan_kernel"
     else:
@@ -255,6 +302,7 @@ def run_ours(args):
     n_res = int(max(2, min(nrec, (free_b * 0.55) // rec_bytes)))
     shape3 = (nz - 1, ny, nx)
     vmask = torch.from_numpy(m.vmask[:-1].astype(np.float32)).cuda()
+    tmask = tbase = sbase = None
     if sig:
         tmask = torch.from_numpy(m.tmask[:-1].astype(np.float32)).cuda()
         z = torch.from_numpy(m.gdept_1d[:-1].astype(np.float32)).cuda()[:, None, None]
@@ -271,9 +319,22 @@ def run_ours(args):
         else:
             recs.append((v,))
     del vmask
-    outs = [torch.empty((nrec,) + out_shape, dtype=torch.float64, device="cuda") for _ in range(2)]
+    outs = [torch.zeros((nrec,) + out_shape, dtype=torch.float64, device="cuda") for _ in range(2)]
     st = torch.cuda.Stream()
     comm = torch.cuda.Stream()
+
+    # ---- the slab gather to rank 0 (the only communication of the path): records go in a few groups, each group's
+    # slabs right behind its kernels on a side stream, into receive buffers allocated ONCE -- only the last group of the
+    # last step is not overlapped by kernels
+    ngroups = 1 if world == 1 else max(1, min(4, nrec // 2))
+    gb = [(g * nrec) // ngroups for g in range(ngroups + 1)]
+    recv, full = None, None
+    if world > 1 and rank == 0:
+        gmax = max(gb[g + 1] - gb[g] for g in range(ngroups))
+        recv = [torch.empty((gmax,) + out_shape, dtype=torch.float64, device="cuda") for _ in range(world)]
+        if band:
+            full = torch.empty((nrec, nyg) + out_shape[1:], dtype=torch.float64, device="cuda")
+    gather_events = []
 
     def launch(rec, o):
         if sig:
@@ -283,16 +344,20 @@ def run_ours(args):
 
     def kernel_step(i):
         o = outs[i & 1]
-        with torch.cuda.stream(st):
-            for r in range(nrec):
-                launch(recs[r % n_res], o[r])
-        if world > 1:  # C1: slab gather to rank 0 on a side stream behind this step's kernels
-            comm.wait_stream(st)
-            with torch.cuda.stream(comm):
-                if band:
-                    shard.gather_band_slabs(o, nyg, row_dim=1)
-                else:   # every rank owns `nrec` records of its own: equal slabs, plain gather
-                    dist.gather(o, [torch.empty_like(o) for _ in range(world)] if rank == 0 else None, dst=0)
+        for g in range(ngroups):
+            with torch.cuda.stream(st):
+                for r in range(gb[g], gb[g + 1]):
+                    launch(recs[r % n_res], o[r])
+            if world > 1:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                with torch.cuda.stream(comm):
+                    comm.wait_event(ev)
+                    part = o[gb[g]:gb[g + 1]]
+                    dist.gather(part, [b[: part.shape[0]] for b in recv] if rank == 0 else None, dst=0)
+                    if band and rank == 0:   # unpack the padded bands into the (record, j, bin, basin) array the writer wants
+                        for rr, (b0, b1) in enumerate(bands):
+                            full[gb[g]:gb[g + 1], b0:b1].copy_(recv[rr][: part.shape[0], : b1 - b0])
 
     def sync_all():
         st.synchronize()
@@ -302,56 +367,61 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    with ClockSampler(local) as clk:
-        for i in range(args.warmup):
-            kernel_step(i)
-        sync_all()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = lib.launch_count()
-        ev0.record(st)
-        for i in range(args.steps):
-            kernel_step(i)
-        if world > 1:
-            st.wait_stream(comm)   # the timed region ends when the last gather has landed on rank 0
-        ev1.record(st)
-        sync_all()
-        launches = lib.launch_count() - l0
-        ms_total = ev0.elapsed_time(ev1)
-        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-        ms_step = ms_total / args.steps
-        value = cells_step_global / (ms_step * 1e-3)
+    for i in range(warmup):
+        kernel_step(i)
+    sync_all()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = lib.launch_count()
+    ev0.record(st)
+    for i in range(steps):
+        kernel_step(i)
+    if world > 1:
+        st.wait_stream(comm)   # the timed region ends when the last gather has landed on rank 0
+    ev1.record(st)
+    sync_all()
+    launches = lib.launch_count() - l0
+    ms_total = cx.max_over_ranks(ev0.elapsed_time(ev1))
+    ms_step = ms_total / steps
+    value = cells_step_global / (ms_step * 1e-3)
 
-        # ---- roofline of the workload's kernel: algorithmic bytes per launch / average launch time (same events)
-        hbm_peak, peak_src = peaks()
-        ms_launch = ms_total / (args.steps * nrec)
-        achieved = bytes_launch / (ms_launch * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "kernel": kname, "bytes_per_launch": bytes_launch, "ms_per_launch": ms_launch,
-                    "peak_source": peak_src, "frac_of_8TBps_spec": achieved / 8000.0,
-                    "note": "per-GPU figure; at N>1 the launch time includes the overlapped NCCL slab gather",
-                    "peak_kind": "measured device-to-device COPY bandwidth (read + write); a read-only streaming kernel can "
-                                 "exceed it slightly (frac > 1) -- see frac_of_8TBps_spec"}
-        if sig:
-            roofline["second_bound"] = ("instruction issue / fp64 pipe: ~60 instructions (47 fp64) per contributing cell for the "
-                                        "FMA-evaluated EOS with exact fallback, plus the histogram flush; see DESIGN.md")
-        tp = ROOT / "profiles" / ("k2_traffic.json" if sig else "k1_traffic.json")
-        if tp.exists() and spec["grid"] == "ORCA025":
-            try:
-                roofline["traffic"] = json.loads(tp.read_text())["dram_bytes_per_launch"]
-            except Exception:
-                pass
+    # ---- roofline of the workload's kernel: algorithmic bytes per launch / average launch time (same events)
+    hbm_peak = cx.hbm_peak
+    ms_launch = ms_total / (steps * nrec)
+    achieved = bytes_launch / (ms_launch * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "kernel": kname, "bytes_per_launch": bytes_launch, "ms_per_launch": ms_launch,
+                "peak_source": cx.peak_src, "frac_of_8TBps_spec": achieved / 8000.0,
+                "note": "per-GPU figure; at N>1 the launch time includes the overlapped NCCL slab gather",
+                "peak_kind": "measured device-to-device COPY bandwidth (read + write); a read-only streaming kernel can "
+                             "exceed it slightly (frac > 1) -- see frac_of_8TBps_spec"}
+    tp = ROOT / "profiles" / ("k2_traffic.json" if sig else "k1_traffic.json")
+    if tp.exists() and spec["grid"] == "ORCA025" and not band:
+        try:
+            tj = json.loads(tp.read_text())
+            roofline["traffic"] = tj["dram_bytes_per_launch"]
+            roofline["traffic_source"] = "committed ncu capture of this kernel on this grid (%s), not a counter of this run" % tp.name
+            if sig and "warp_inst_per_launch" in tj:
+                roofline["warp_inst_per_launch"] = tj["warp_inst_per_launch"]
+        except Exception:
+            pass
 
-        # ---- end to end through the record pipeline: pinned host -> H2D (copy stream) -> kernel -> D2H
+    # ---- end to end through the record pipeline: pinned host -> H2D (copy stream) -> kernel -> D2H
+    e2e = None
+    host, res = [], None
+    if do_e2e:
         n_host = min(nrec, 6 if not sig else 3)
         host = [[lib.PinnedArray(shape3, np.float32) for _ in range(narr)] for _ in range(n_host)]
         for h, r in zip(host, (recs * n_host)[:n_host]):
             for ha, ra in zip(h, r):
                 ha.array[...] = ra.cpu().numpy()
-        res = lib.PinnedArray((3,) + out_shape, np.float64)
+        eshape = (ny,) + out_shape[1:] if sig else out_shape
+        res = lib.PinnedArray((3,) + eshape, np.float64)
         nslots = 3
+        # the platform's ceiling for the input leg: all ranks copy pinned records to their GPUs at once, nothing else running
+        if world > 1:
+            dist.barrier()
+        h2d_gbs = lib.h2d_probe(host[0][0], reps=6)
+        h2d_all = cx.sum_over_ranks(h2d_gbs)
 
         def e2e_step():
             pend = []
@@ -369,7 +439,7 @@ def run_ours(args):
             for s in pend:
                 (lib.cdfmocsig_fetch if sig else lib.cdfmoc_fetch)(s, res.array[s])
 
-        e2e_steps = max(1, min(args.steps, 3))
+        e2e_steps = max(1, min(steps, 3))
         e2e_step()
         lib.synchronize()
         if world > 1:
@@ -379,21 +449,24 @@ def run_ours(args):
             e2e_step()
         lib.synchronize()
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    e2e = {"value": cells_step_global * e2e_steps / dt, "unit": "cells/s", "h2d_bytes_per_step": nrec * rec_bytes,
-           "d2h_bytes_per_step": nrec * int(np.prod(out_shape)) * 8, "steps": e2e_steps,
-           "ms_per_step": dt / e2e_steps * 1e3,
-           "path": "cdf%s_gpu_submit/_fetch, 3 slots, pinned host records (per rank)" % ("mocsig" if sig else "moc"),
-           "cpu_affinity_rank0": numa}
+        dt = cx.max_over_ranks(time.perf_counter() - t0)
+        h2d_bytes = nrec * rec_bytes
+        gbs_all = world * h2d_bytes * e2e_steps / dt / 1e9
+        e2e = {"value": cells_step_global * e2e_steps / dt, "unit": "cells/s", "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": nrec * int(np.prod(eshape)) * 8, "steps": e2e_steps,
+               "ms_per_step": dt / e2e_steps * 1e3,
+               "path": "cdf%s_gpu_submit/_fetch, 3 slots, pinned host records (per rank)" % ("mocsig" if sig else "moc"),
+               "h2d_gbs_all_ranks": gbs_all,
+               "h2d_ceiling_gbs_all_ranks": h2d_all,
+               "frac_of_h2d_ceiling": gbs_all / h2d_all if h2d_all > 0 else None,
+               "h2d_ceiling_note": "all ranks copying one pinned record to their GPU at once (cudaMemcpyAsync, no kernels): what "
+                                   "this host's PCIe / memory system delivers; the pipeline is bound by it, not by the kernels",
+               "cpu_affinity_rank0": cx.numa}
 
     # ---- parity spot check of the timed kernel against the oracle (sampled latitude rows of one record)
     parity = None
     if rank == 0:
-        got_all = outs[(args.steps - 1) & 1][0].cpu().numpy()
+        got_all = outs[(steps - 1) & 1][0].cpu().numpy()
         arrs = [a.cpu().numpy() for a in recs[0]]
         errs, ok = [], True
         cand = np.unique(np.linspace(1, ny - 2, 5).astype(int)) if ny > 4 else np.arange(ny)
@@ -408,12 +481,15 @@ def run_ours(args):
             d = np.abs(got - ref)
             errs.append(float(d.max()))
             ok = ok and bool(np.all(d <= np.maximum(1e-9 * np.abs(ref), 1e-6)))
-        parity = {"rows_checked": int(len(cand)), "max_abs_err_sv": max(errs), "within_tolerance": ok}
+        parity = {"rows_checked": int(len(cand)), "max_abs_err_sv": max(errs), "within_tolerance": ok,
+                  "tolerance": "1e-9 relative or 1e-6 Sv"}
+        if band and full is not None:   # the gathered array on rank 0 holds every band: rank 0's own rows must be in place
+            parity["gathered_equals_local"] = bool(torch.equal(full[0, j0:j1], outs[(steps - 1) & 1][0, : j1 - j0]))
 
     # ---- cdfmocsig only: the same kernel on T/S as smooth as the stratification (no cell-to-cell noise), one untimed
     # and one timed pass over the resident records.  The headline `value` stays the white-noise case (worst case for the
-    # histogram flush); this shows the other end of the range.  Done last: it overwrites the resident T/S.
-    if sig and world == 1:
+    # density-class run merge); this shows the other end of the range.  Done last: it overwrites the resident T/S.
+    if sig and do_smooth:
         for r, rec in enumerate(recs):
             rec[1].copy_((tbase + 0.5 * np.sin(0.3 * r)).mul_(tmask))
             rec[2].copy_(sbase * tmask)
@@ -426,51 +502,148 @@ def run_ours(args):
                     launch(recs[r % n_res], outs[0][r])
                 e1.record(st)
             st.synchronize()
-        ms_s = e0.elapsed_time(e1) / nrec
+        ms_s = cx.max_over_ranks(e0.elapsed_time(e1)) / nrec
         ach_s = bytes_launch / (ms_s * 1e-3) / 1e9
         roofline["smooth_ts"] = {"ms_per_launch": ms_s, "achieved": ach_s, "frac": ach_s / hbm_peak,
                                  "note": "same launches with ts_noise = 0 (T/S as smooth as the stratification)"}
-    if sig:
-        del tmask, tbase, sbase
+    filt = lib.cdfmocsig_filter_info() if sig else None
 
-    if rank == 0 and world == 1:   # the CPU baseline uses every host core, not only the GPU-local ones
-        try:
-            os.sched_setaffinity(0, ALL_CPUS)
-        except Exception:
-            pass
-    cb = cpu_baseline(spec, m, ib, e3m) if (rank == 0 and world == 1) else None
-    if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "strong" if band else "weak", "vs_baseline": None, "dtype": "f32 products, f64 sums",
-                "data": "synthetic",
-                "config": {"workload": args.workload, "grid": spec["grid"], "nx": nxg, "ny": nyg, "nz": nzg,
-                           "basins": nb, "records_per_step_per_gpu": nrec, "resident_records": n_res,
-                           "rows_per_gpu": ny,
-                           "l2": "inputs (%.1f GB resident per GPU) are far larger than the 126 MB L2; no flush needed"
-                                 % (n_res * rec_bytes / 1e9),
-                           "sharding": ("latitude bands + NCCL slab gather" if band else
-                                        "time (each rank owns its own records) + NCCL slab gather") if world > 1
-                           else "single GPU",
-                           "wet_fraction": m.wet_fraction},
-                "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
-                "parity_check": parity}
-        if sig:
-            line["config"].update({"pref": spec["pref"], "sigmin": spec["bins"][0], "sigstp": spec["bins"][1],
-                                   "nbins": spec["bins"][2], "eos": "EOS80 polynomial",
-                                   "ts_noise_K": args.ts_noise,
-                                   "ts_noise": "white, cell to cell (0.15 K: every neighbour in another density class, the "
-                                               "worst case for run merging; 0: as smooth as the stratification)"})
-        if cb:
-            line["cpu_baseline"] = cb
-        print(json.dumps(line))
+    cb = None
+    if do_cpu and rank == 0 and world == 1:
+        cb = cpu_baseline(spec, m, ib, e3m)
+    rec = {"workload": workload, "value": value, "unit": "cells/s", "ms_per_step": ms_step, "steps": steps, "warmup": warmup,
+           "scaling": "strong" if band else "weak", "roofline": roofline, "gpu_launches": int(launches),
+           "parity_check": parity,
+           "config": {"workload": workload, "grid": spec["grid"], "nx": nxg, "ny": nyg, "nz": nzg,
+                      "basins": nb, "records_per_step_per_gpu": nrec, "resident_records": n_res, "rows_per_gpu": ny,
+                      "l2": "inputs (%.1f GB resident per GPU) are far larger than the 126 MB L2; no flush needed"
+                            % (n_res * rec_bytes / 1e9),
+                      "sharding": ("latitude bands + NCCL slab gather" if band else
+                                   "time (each rank owns its own records) + NCCL slab gather") if world > 1 else "single GPU",
+                      "gather": ("%d group(s) per step behind their kernels, preallocated receive buffers, "
+                                 "NCCL_MAX_NCHANNELS=%s" % (ngroups, os.environ.get("NCCL_MAX_NCHANNELS"))) if world > 1 else None,
+                      "wet_fraction": m.wet_fraction}}
+    if e2e:
+        rec["e2e"] = e2e
+    if cb:
+        rec["cpu_baseline"] = cb
+    if sig:
+        rec["config"].update({"pref": spec["pref"], "sigmin": spec["bins"][0], "sigstp": spec["bins"][1],
+                              "nbins": spec["bins"][2], "eos": "EOS80 polynomial", "ts_noise_K": args.ts_noise,
+                              "ts_noise": "white, cell to cell (0.15 K: every neighbour in another density class, the "
+                                          "worst case for run merging; 0: as smooth as the stratification)",
+                              "bin_function": filt})
     for h in host:
         for ha in h:
             ha.free()
-    res.free()
-    lib.finalize()
+    if res is not None:
+        res.free()
+    (lib.cdfmocsig_teardown if sig else lib.cdfmoc_teardown)()
+    del recs, outs, recv, full, tmask, tbase, sbase
+    torch.cuda.empty_cache()
+    return rec
+
+
+def issue_bound(cx: Ctx, k2: dict):
+    """K2's second bound (the arithmetic ceiling must be measured before K2 is called HBM-bound).
+    The bin function runs in packed fp32, so the ceiling is instruction ISSUE: the kernel's warp-instructions per launch
+    (committed ncu count) against the issue rate this device sustains on an fp32-FMA / integer mix, measured here."""
+    mb = cx.lib.microbench()
+    rl = k2["roofline"]
+    out = {"microbench": mb,
+           "note": "warp-instructions per clock and SM with 8 warps per scheduler and 8 independent chains per thread; "
+                   "dfma = the fp64 pipe the reference-exact tiers use, ffma2 = the packed fp32 FMA of the fp32 tier"}
+    wi = rl.get("warp_inst_per_launch")
+    if wi:
+        rate = mb["ffma_int_mix"]["ginst_per_s"] * 1e9
+        ms_issue = wi / rate * 1e3
+        ms_hbm = rl["bytes_per_launch"] / (cx.hbm_peak * 1e9) * 1e3
+        out.update({"warp_inst_per_launch": wi, "issue_ms_per_launch": ms_issue, "hbm_ms_per_launch": ms_hbm,
+                    "binding": "issue" if ms_issue > ms_hbm else "hbm",
+                    "frac_of_min_bound": max(ms_issue, ms_hbm) / rl["ms_per_launch"],
+                    "frac_of_min_bound_smooth": max(ms_issue, ms_hbm) / rl["smooth_ts"]["ms_per_launch"] if "smooth_ts" in rl else None})
+    return out
+
+
+def e2e_files(cx: Ctx, nrec=12):
+    """End to end INCLUDING NetCDF I/O: a synthetic ORCA025 gridV file + mesh / mask files on tmpfs -> the cdfmoc_gpu
+    command-line twin (a process of its own: CUDA start-up, mesh and mask read, setup, record pipeline, moc.nc)."""
+    import tempfile
+    from cdftools_b200 import build, ncfiles, synth
+    tools = build.build_host()
+    m = synth.make_mesh("ORCA025")
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if Path("/dev/shm").exists() else None) as d:
+        ncfiles.write_mesh(m, d)
+        ncfiles.write_gridv(m, Path(d) / "gridV.nc", nrec)
+        size = (Path(d) / "gridV.nc").stat().st_size
+        env = dict(os.environ, CDFGPU_DEVICE=str(cx.local))
+        subprocess.run([tools["cdfmoc_gpu"], "-v", "gridV.nc"], cwd=d, check=True, capture_output=True, env=env)   # warm page cache
+        t0 = time.perf_counter()
+        r = subprocess.run([tools["cdfmoc_gpu"], "-v", "gridV.nc"], cwd=d, check=True, capture_output=True, env=env, text=True)
+        dt = time.perf_counter() - t0
+        phases = [l for l in (r.stderr or "").splitlines() if l.startswith("cdfmoc_gpu: phase")]
+    cells = nrec * m.nx * m.ny * m.nz
+    return {"tool": "cdfmoc_gpu -v gridV.nc", "grid": "ORCA025", "records": nrec, "gridV_bytes": size, "wall_s": dt,
+            "value": cells / dt, "unit": "cells/s", "phases": phases,
+            "note": "whole process wall clock: CUDA init, mesh / mask files, setup, then fread of raw big-endian records -> "
+                    "pinned -> H2D -> GPU byte swap -> K1 -> D2H -> moc.nc; files on tmpfs"}
+
+
+def run_ours(args):
+    cx = Ctx(args)
+    rank, world = cx.rank, cx.world
+    with ClockSampler(cx.local) as clk:
+        main = measure(cx, args.workload, args.steps, args.warmup, do_e2e=True, do_cpu=True)
+    line = None
+    if rank == 0:
+        spec = WORKLOADS[args.workload]
+        line = {"metric": METRIC, "value": main["value"], "unit": "cells/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+                "scaling": main["scaling"], "vs_baseline": None, "dtype": "f32 products, f64 sums", "data": "synthetic",
+                "config": main["config"], "roofline": main["roofline"], "e2e": main.get("e2e"),
+                "gpu_launches": main["gpu_launches"], "clocks": clk.summary(), "parity_check": main["parity_check"]}
+        if "cpu_baseline" in main:
+            line["cpu_baseline"] = main["cpu_baseline"]
+
+    # ---- sub-records: the other BASELINE.json configurations, each to the same parity + roofline bar, while the budget lasts
+    subs = {}
+
+    def sub(name, fn, need_s):
+        if args.no_subrecords or args.workload != DEFAULT_WORKLOAD:
+            return
+        go = cx.elapsed() + need_s < args.budget_s
+        if world > 1:   # every rank takes the same decision
+            t = cx.torch.tensor([1.0 if go else 0.0], device="cuda", dtype=cx.torch.float64)
+            cx.dist.all_reduce(t, op=cx.dist.ReduceOp.MIN)
+            go = bool(t.item() > 0.5)
+        if not go:
+            subs[name] = {"skipped": "time budget (%.0f s used of %.0f)" % (cx.elapsed(), args.budget_s)}
+            return
+        try:
+            subs[name] = fn()
+        except Exception as e:   # a sub-record must never take the headline line down with it
+            if world > 1:
+                raise
+            subs[name] = {"error": repr(e)[:300]}
+
+    if world == 1:
+        def k2():
+            r = measure(cx, "cdfmocsig-ORCA025-L75-sigma0-104bins-73rec", steps=3, warmup=3, nrec=12, do_e2e=False)
+            r["second_bound"] = issue_bound(cx, r)
+            return r
+        sub("k2_config3", k2, 60)
+        sub("e2e_files", lambda: e2e_files(cx), 90)
+    else:
+        sub("config4", lambda: measure(cx, "cdfmoc-ORCA12-L75-46rec-5basins", steps=3, warmup=3, nrec=6, do_e2e=False), 240)
+        sub("config5", lambda: measure(cx, "cdfmocsig-ORCA12-L75-sigma2-158bins-8rec-bands", steps=3, warmup=3, nrec=4,
+                                       do_e2e=False), 120)
+    if rank == 0:
+        line["sub_records"] = subs
+        line["wall_s"] = cx.elapsed()
+        print(json.dumps(line))
+    cx.lib.finalize()
     if world > 1:
-        dist.destroy_process_group()
+        cx.dist.destroy_process_group()
 
 
 def main():
@@ -483,6 +656,11 @@ def main():
     ap.add_argument("--ts-noise", type=float, default=0.15,
                     help="cdfmocsig workloads: amplitude (K) of the cell-to-cell white noise on T (x0.2 on S); 0.15 is the "
                          "worst case for density-class run merging, 0 gives fields as smooth as the stratification")
+    ap.add_argument("--budget-s", type=float, default=420.0,
+                    help="wall-clock budget of this process: a sub-record (the other BASELINE configurations) is only started "
+                         "while its estimated duration still fits")
+    ap.add_argument("--no-subrecords", action="store_true", help="headline workload only")
+    ap.add_argument("--nccl-channels", type=int, default=4, help="NCCL_MAX_NCHANNELS for the slab gather (unless already set)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

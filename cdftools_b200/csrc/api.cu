@@ -15,6 +15,7 @@
 #include "moc_decomp.cuh"
 #include "zonal_kernels.cuh"
 #include "transig_kernels.cuh"
+#include "microbench.cuh"
 
 namespace cdfgpu {
 
@@ -627,10 +628,79 @@ int cdfgpu_pinned_free(void *p)
     if (p) CDF_CUDA(cudaFreeHost(p));
     return CDFGPU_OK;
 }
+// Platform ceiling of the record pipeline's input leg: `reps` asynchronous copies of a pinned host buffer to device memory
+// on the library's copy stream, nothing else running.  gbs = GB/s of this process (bench.py sums the ranks).
+int cdfgpu_h2d_probe(const void *pinned, size_t nbytes, int reps, double *gbs)
+{
+    REQUIRE_INIT();
+    REQUIRE(pinned && nbytes > 0 && reps > 0 && gbs, CDFGPU_ERR_ARG, "cdfgpu_h2d_probe: bad argument");
+    void *d = nullptr;
+    CDF_CUDA(cudaMalloc(&d, nbytes));
+    cudaEvent_t e0, e1;
+    CDF_CUDA(cudaEventCreate(&e0));
+    CDF_CUDA(cudaEventCreate(&e1));
+    CDF_CUDA(cudaMemcpyAsync(d, pinned, nbytes, cudaMemcpyHostToDevice, g.s_copy));   // warm-up
+    CDF_CUDA(cudaEventRecord(e0, g.s_copy));
+    for (int r = 0; r < reps; ++r) CDF_CUDA(cudaMemcpyAsync(d, pinned, nbytes, cudaMemcpyHostToDevice, g.s_copy));
+    CDF_CUDA(cudaEventRecord(e1, g.s_copy));
+    CDF_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CDF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *gbs = (double)nbytes * reps / (ms * 1e-3) / 1e9;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    return CDFGPU_OK;
+}
 unsigned long long cdfgpu_launch_count(void) { return g.launches; }
 int cdfgpu_set_input_big_endian(int on)
 {
     g.big_endian_input = on != 0;
+    return CDFGPU_OK;
+}
+
+// kind: 0 DFMA, 1 FFMA, 2 FFMA2 (packed fp32), 3 integer (LOP3 + shift-add), 4 FFMA alternating with integer operations.
+// out[0] = warp-instructions per clock and SM (the slowest CTA's own clock64 window), out[1] = 1e9 warp-instructions / s
+// over the chip (CUDA events), out[2] = SM clock in MHz implied by the two.
+int cdfgpu_microbench(int kind, double *out3)
+{
+    REQUIRE_INIT();
+    REQUIRE(kind >= 0 && kind <= 4 && out3, CDFGPU_ERR_ARG, "cdfgpu_microbench: kind must be 0..4");
+    const int iters = 20000, nblk = g.sm_count;
+    unsigned long long *d_cyc = nullptr;
+    double *d_sink = nullptr;
+    CDF_CUDA(cudaMalloc(&d_cyc, nblk * sizeof(unsigned long long)));
+    CDF_CUDA(cudaMalloc(&d_sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CDF_CUDA(cudaEventCreate(&e0));
+    CDF_CUDA(cudaEventCreate(&e1));
+    float ms = 0.f;
+    for (int rep = 0; rep < 2; ++rep) {   // first pass warms up
+        CDF_CUDA(cudaEventRecord(e0, g.s_compute));
+        switch (kind) {
+        case kMbDfma: microbench_kernel<kMbDfma><<<nblk, 1024, 0, g.s_compute>>>(iters, 1.0f, d_cyc, d_sink); break;
+        case kMbFfma: microbench_kernel<kMbFfma><<<nblk, 1024, 0, g.s_compute>>>(iters, 1.0f, d_cyc, d_sink); break;
+        case kMbFfma2: microbench_kernel<kMbFfma2><<<nblk, 1024, 0, g.s_compute>>>(iters, 1.0f, d_cyc, d_sink); break;
+        case kMbIadd: microbench_kernel<kMbIadd><<<nblk, 1024, 0, g.s_compute>>>(iters, 1.0f, d_cyc, d_sink); break;
+        default: microbench_kernel<kMbMixed><<<nblk, 1024, 0, g.s_compute>>>(iters, 1.0f, d_cyc, d_sink); break;
+        }
+        CDF_CUDA(cudaGetLastError());
+        ++g.launches;
+        CDF_CUDA(cudaEventRecord(e1, g.s_compute));
+        CDF_CUDA(cudaEventSynchronize(e1));
+        CDF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    std::vector<unsigned long long> cyc(nblk);
+    CDF_CUDA(cudaMemcpy(cyc.data(), d_cyc, nblk * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned long long mx = 1;
+    for (auto c : cyc) mx = std::max(mx, c);
+    // per trip: kinds 0..2 issue 32 operations, kind 3 issues 64 (two per step), kind 4 issues 48 (fma + xor + add per step)
+    const double per_trip = kind == kMbIadd ? 64.0 : kind == kMbMixed ? 48.0 : 32.0;
+    const double winst_per_sm = (double)iters * per_trip * 32.0;   // 32 warps per CTA
+    out3[0] = winst_per_sm / (double)mx;
+    out3[1] = winst_per_sm * nblk / (ms * 1e-3) / 1e9;
+    out3[2] = (double)mx / (ms * 1e-3) / 1e6;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_cyc); cudaFree(d_sink);
     return CDFGPU_OK;
 }
 

@@ -32,8 +32,10 @@ SIGNATURES = {
     "cdfgpu_pinned_alloc": (C.c_void_p, [C.c_size_t]),
     "cdfgpu_pinned_free": (C.c_int, [C.c_void_p]),
     "cdfgpu_launch_count": (C.c_ulonglong, []),
+    "cdfgpu_h2d_probe": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
     "cdfgpu_set_input_big_endian": (C.c_int, [C.c_int]),
     "cdfgpu_set_device_inputs_ready": (C.c_int, [C.c_int]),
+    "cdfgpu_microbench": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "cdfmoc_gpu_setup": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cdfmoc_gpu_set_e3v": (C.c_int, [C.c_void_p]),
     "cdfmoc_gpu_submit": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
@@ -296,6 +298,23 @@ def cdfmocsig_compute_device(d_zv, d_zt, d_zs, d_dmoc, d_zveiv=None, d_e3v_vvl=N
 def set_device_inputs_ready(on: bool = True):
     """Records handed to *_compute_device on a caller stream are resident and synchronised (see cdfgpu.h)."""
     _chk(load().cdfgpu_set_device_inputs_ready(1 if on else 0), "cdfgpu_set_device_inputs_ready")
+
+
+def h2d_probe(pinned: "PinnedArray", reps: int = 4) -> float:
+    """GB/s of plain pinned-host -> device copies on the copy stream (the platform ceiling of *_submit's input leg)."""
+    v = C.c_double()
+    _chk(load().cdfgpu_h2d_probe(C.c_void_p(pinned.addr), C.c_size_t(pinned.nbytes), int(reps), C.byref(v)), "cdfgpu_h2d_probe")
+    return float(v.value)
+
+
+def microbench() -> dict:
+    """Measured issue ceilings: {name: (warp-instructions / clock / SM, Ginst/s over the chip, SM MHz)}."""
+    out = {}
+    for kind, name in enumerate(("dfma", "ffma", "ffma2", "int", "ffma_int_mix")):
+        v = (C.c_double * 3)()
+        _chk(load().cdfgpu_microbench(kind, v), "cdfgpu_microbench")
+        out[name] = {"winst_per_clk_sm": v[0], "ginst_per_s": v[1], "sm_mhz": v[2]}
+    return out
 
 
 def cdfmocsig_bins_device_stats(d_zt, d_zs, d_ibin, stream=None):

@@ -221,3 +221,26 @@ def basin_mask_inputs(mesh: Mesh, with_basins: bool = True):
     if not with_basins:
         return v1, None, None, None
     return v1, mesh.tmaskatl, mesh.tmaskind, mesh.tmaskpac
+
+
+def setup_masks(mesh: Mesh, with_basins: bool = True) -> np.ndarray:
+    """ibmask (ny,nx,nb) INTEGER(2) as the host program hands it to *_setup: what src/cdfmoc.f90:325-336 assembles from
+    the planes of basin_mask_inputs (global = vmask(k=1) with i=1 and i=nx zeroed, atl, inp = min(1, pac+ind), ind, pac)."""
+    v1, atl, ind, pac = basin_mask_inputs(mesh, with_basins)
+    ny, nx = v1.shape
+    nb = 5 if with_basins else 1
+    m = np.zeros((ny, nx, nb), np.int16)
+    m[:, :, 0] = v1.astype(np.int16)
+    if with_basins:
+        m[:, :, 1] = atl.astype(np.int16)
+        m[:, :, 3] = ind.astype(np.int16)
+        m[:, :, 4] = pac.astype(np.int16)
+        m[:, :, 2] = np.minimum(1, m[:, :, 4] + m[:, :, 3]).astype(np.int16)
+    m[:, 0, 0] = 0
+    m[:, nx - 1, 0] = 0
+    return m
+
+
+def setup_e3v_masked(mesh: Mesh) -> np.ndarray:
+    """e3v (nz,ny,nx) REAL(4) already multiplied by vmask, as get_e3v returns it (src/cdfmoc.f90:590-594)."""
+    return (mesh.e3v_0 * mesh.vmask.astype(np.float32)).astype(np.float32)

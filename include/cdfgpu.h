@@ -63,6 +63,9 @@ int cdfgpu_abi_version(void);
 /* Page-locked host buffers for NF90_GET_VAR to fill (Fortran: c_f_pointer onto the returned address). */
 void *cdfgpu_pinned_alloc(size_t nbytes);
 int cdfgpu_pinned_free(void *p);
+/* Ceiling of the record pipeline's input leg on this platform: GB/s of `reps` asynchronous copies of a pinned host buffer
+ * to the device on the library's copy stream, with nothing else running. */
+int cdfgpu_h2d_probe(const void *pinned, size_t nbytes, int reps, double *gbs);
 /* Number of kernels this library has launched since cdfgpu_init (bench.py's gpu_launches). */
 unsigned long long cdfgpu_launch_count(void);
 /* K3: records handed to *_submit are RAW big-endian NetCDF-3 bytes (what fread delivers; the XDR decode libnetcdf
@@ -76,6 +79,10 @@ int cdfgpu_set_input_big_endian(int on);
  * caller guarantees resident, synchronised inputs and gets the overlap.  Launches on the library's own streams are ordered
  * by the library itself. */
 int cdfgpu_set_device_inputs_ready(int on);
+/* Instruction-issue ceilings of the device, measured (the second bound of K2 beside HBM, bench.py): kind 0 = DFMA, 1 = FFMA,
+ * 2 = FFMA2 (packed fp32), 3 = integer, 4 = FFMA and integer alternating.  out3 = { warp-instructions per clock and SM,
+ * 1e9 warp-instructions per second over the chip, SM clock (MHz) during the run }. */
+int cdfgpu_microbench(int kind, double *out3);
 
 /* ---- cdfmoc: depth-space MOC ------------------------------------------------------------------------------
  * setup   replaces the one-time part of src/cdfmoc.f90:306,325-336,343-348:

@@ -37,6 +37,8 @@ def lib():
         _LIB.oracle_eos_dlr.restype = C.c_double
         _LIB.oracle_eos_dlr.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int]
         _LIB.oracle_num_threads.restype = C.c_int
+        _LIB.oracle_set_num_threads.restype = None
+        _LIB.oracle_set_num_threads.argtypes = [C.c_int]
     return _LIB
 
 
@@ -46,6 +48,11 @@ def _p(a, t):
 
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def set_num_threads(n: int) -> None:
+    """OpenMP threads of the following calls (a launcher may have exported OMP_NUM_THREADS=1, as torchrun does)."""
+    lib().oracle_set_num_threads(int(n))
 
 
 def num_threads() -> int:

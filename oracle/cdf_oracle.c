@@ -41,6 +41,11 @@
 
 int oracle_abi_version(void) { return 1; }
 
+void oracle_set_num_threads(int n)
+{
+    if (n > 0) omp_set_num_threads(n);
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP

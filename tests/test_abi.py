@@ -62,7 +62,7 @@ def test_fortran_module_binds_the_host_facing_abi():
     fortran = (ROOT / "cdftools_b200" / "fortran" / "cdfgpu_mod.f90").read_text()
     bound = set(re.findall(r"NAME='(\w+)'", fortran))
     device_side_or_c_only = {"cdfmoc_gpu_compute_device", "cdfmocsig_gpu_compute_device", "cdfmocsig_gpu_bins_device",
-                             "cdfmocsig_gpu_bins_device_stats", "cdfgpu_set_device_inputs_ready",
+                             "cdfmocsig_gpu_bins_device_stats", "cdfgpu_set_device_inputs_ready", "cdfgpu_microbench", "cdfgpu_h2d_probe",
                              "cdfgpu_strerror", "cdfgpu_launch_count"}
     declared = _declared()
     assert bound <= declared, bound - declared
