@@ -7,9 +7,6 @@
 
 #include "common.cuh"
 #include "moc_kernel.cuh"
-#include "moc_kernel_tma.cuh"
-#include "moc_kernel_pipe.cuh"
-#include "moc_kernel_class.cuh"
 #include "eos_device.cuh"
 #include "mocsig_kernel.cuh"
 #include "moc_decomp.cuh"
@@ -78,9 +75,9 @@ static int swap_record(float *d, size_t n, cudaStream_t st)
 
 static int make_ws(Workspace &w, int ny)
 {
-    CDF_CUDA(cudaMalloc(&w.d_tickets, (3 * kTicketShards * kTicketStride + 64) * sizeof(int)));   // + the TMA kernel's own pair
+    CDF_CUDA(cudaMalloc(&w.d_tickets, 3 * kTicketShards * kTicketStride * sizeof(int)));
     CDF_CUDA(cudaMalloc(&w.d_col, (size_t)ny * sizeof(int)));
-    CDF_CUDA(cudaMemsetAsync(w.d_tickets, 0, (3 * kTicketShards * kTicketStride + 64) * sizeof(int), g.s_compute));
+    CDF_CUDA(cudaMemsetAsync(w.d_tickets, 0, 3 * kTicketShards * kTicketStride * sizeof(int), g.s_compute));
     CDF_CUDA(cudaMemsetAsync(w.d_col, 0, (size_t)ny * sizeof(int), g.s_compute));
     w.parity = 0;
     w.gen3 = 0;
@@ -160,90 +157,36 @@ struct MocPlan {
     std::vector<double> dec_dlh, dec_dlref;
     Workspace ws_int, ws_ext;
     Slot slots[CDFGPU_MAX_SLOTS];
-    int grid = 0;
+    int grid = 0, grid_batch = 0;
     size_t smem = 0;
-    int variant = 0;       // register-staged kernel: unroll / occupancy variant ($CDFGPU_K1_VARIANT, experiments)
-    // class-run kernel (moc_kernel_class.cuh): 0/1 masks with <= 8 distinct non-zero mask tuples
-    bool use_class = false;
-    int k1_nclass = 0, segpitch = 0, class_grid = 0;
-    uint32_t *d_classw = nullptr;
-    uint8_t *d_segtab = nullptr;
-    std::vector<uint8_t> h_cls;   // class of every (j,i), kept for -vvl rebuilds of the segment table
-    std::vector<float> h_e1v;     // e1v, likewise
-    bool use_tma = false;  // $CDFGPU_K1=tma selects the TMA-fed class-sum kernel
-    bool pdl = true;       // programmatic dependent launch of the default kernel ($CDFGPU_K1_PDL=0 switches it off)
-    // TMA path (0/1 masks, <= 8 distinct mask tuples, finite area)
-    uint8_t *d_classes = nullptr;
-    int nclass = 0, lane_cells = 0, ntile = 0, cpitch = 0, tma_warps = 0, tma_grid = 0, tma_chunk = 1;
-    size_t tma_smem = 0;
+    bool pdl = true;       // programmatic dependent launch ($CDFGPU_K1_PDL=0 switches it off)
+    // batched launches (cdfmoc_gpu_compute_device_batch): device arrays of record / slab pointers, column counters
+    const float **d_batch_zv = nullptr;
+    double **d_batch_out = nullptr;
+    int *d_batch_col = nullptr;
+    int batch_cap = 0, batch_flip = 0;
     size_t in_elems() const { return (size_t)(nz - 1) * ny * nx; }
     size_t out_elems() const { return (size_t)nz * ny * nb; }
 };
 static MocPlan moc;
 
-// Distinct 0/1 mask tuples -> class index (0 = no basin); 4 pre-shifted byte planes, 255 outside the row.
-// Returns the number of classes, or 0 when the class path does not apply (non-binary masks, > 8 classes).
-static int pack_classes(int nx, int ny, int nb, const int16_t *ibmask, int cpitch, std::vector<uint8_t> &planes,
-                        uint32_t *class_bits)
-{
-    std::vector<uint8_t> cls((size_t)nx * ny);
-    int nclass = 1;
-    class_bits[0] = 0u;
-    for (size_t c = 0; c < (size_t)nx * ny; ++c) {
-        uint32_t bits = 0;
-        for (int b = 0; b < nb; ++b) {
-            const int16_t m = ibmask[c * nb + b];
-            if (m != 0 && m != 1) return 0;
-            if (m) bits |= 1u << b;
-        }
-        int q = 0;
-        while (q < nclass && class_bits[q] != bits) ++q;
-        if (q == nclass) {
-            if (nclass == kTmaMaxClasses) return 0;
-            class_bits[nclass++] = bits;
-        }
-        cls[c] = (uint8_t)q;
-    }
-    planes.assign((size_t)4 * ny * cpitch, (uint8_t)255);
-    for (int s = 0; s < 4; ++s)
-        for (int j = 0; j < ny; ++j)
-            memcpy(planes.data() + ((size_t)s * ny + j) * cpitch + s, cls.data() + (size_t)j * nx, (size_t)nx);
-    return nclass;
-}
-
-template <int NB>
-static int moc_tma_launch_t(const MocTmaParams &p, cudaStream_t st)
-{
-    auto kern = moc_zonal_scan_tma_kernel<NB>;
-    if (moc.tma_grid == 0) {
-        int occ = 0;
-        CDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)moc.tma_smem));
-        CDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, moc.tma_warps * 32, moc.tma_smem));
-        if (occ < 1) return set_error(CDFGPU_ERR_ARG, "cdfmoc: TMA kernel does not fit in shared memory");
-        moc.tma_grid = occ * g.sm_count;
-    }
-    kern<<<moc.tma_grid, moc.tma_warps * 32, moc.tma_smem, st>>>(p);
-    CDF_CUDA(cudaGetLastError());
-    ++g.launches;
-    return CDFGPU_OK;
-}
-
-template <int NB, int UNROLL, int MINB>
+template <int NB, int UNROLL, int MINB, bool BATCH>
 static int moc_launch_v(const MocParams &p, cudaStream_t st)
 {
-    auto kern = moc_zonal_scan_kernel<NB, UNROLL, MINB>;
-    if (moc.grid == 0) {
+    auto kern = moc_zonal_scan_kernel<NB, UNROLL, MINB, BATCH>;
+    int &grid = BATCH ? moc.grid_batch : moc.grid;
+    if (grid == 0) {
         int occ = 0;
         CDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)moc.smem));
         CDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kMocThreads, moc.smem));
         if (occ < 1) return set_error(CDFGPU_ERR_ARG, "cdfmoc: kernel does not fit (nz*nb too large for shared memory)");
-        moc.grid = occ * g.sm_count;
+        grid = occ * g.sm_count;
     }
     if (moc.pdl) {   // programmatic dependent launch: consecutive K1 launches of a stream overlap tail and ramp-up
         MocParams q = p;
         q.pdl = 1;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)moc.grid);
+        cfg.gridDim = dim3((unsigned)grid);
         cfg.blockDim = dim3(kMocThreads);
         cfg.dynamicSmemBytes = moc.smem;
         cfg.stream = st;
@@ -254,25 +197,8 @@ static int moc_launch_v(const MocParams &p, cudaStream_t st)
         cfg.numAttrs = 1;
         CDF_CUDA(cudaLaunchKernelEx(&cfg, kern, q));
     } else {
-        kern<<<moc.grid, kMocThreads, moc.smem, st>>>(p);
+        kern<<<grid, kMocThreads, moc.smem, st>>>(p);
     }
-    CDF_CUDA(cudaGetLastError());
-    ++g.launches;
-    return CDFGPU_OK;
-}
-template <int NB, int U, int S, int MINB, bool BULK = false>
-static int moc_launch_pipe(const MocParams &p, cudaStream_t st)
-{
-    auto kern = moc_zonal_scan_pipe_kernel<NB, U, S, MINB, BULK>;
-    const size_t smem = (size_t)(kMocThreads / 32) * S * (sizeof(MocStage<U>) + sizeof(int4) + sizeof(uint64_t));
-    if (moc.grid == 0) {
-        int occ = 0;
-        CDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kMocThreads, smem));
-        if (occ < 1) return set_error(CDFGPU_ERR_ARG, "cdfmoc: staged kernel does not fit in shared memory");
-        moc.grid = occ * g.sm_count;
-    }
-    kern<<<moc.grid, kMocThreads, smem, st>>>(p);
     CDF_CUDA(cudaGetLastError());
     ++g.launches;
     return CDFGPU_OK;
@@ -280,159 +206,18 @@ static int moc_launch_pipe(const MocParams &p, cudaStream_t st)
 template <int NB>
 static int moc_launch_t(const MocParams &p, cudaStream_t st)
 {
-    if (!p.general) {   // asynchronously staged kernel (moc_kernel_pipe.cuh); non-binary masks keep the literal-chain kernel
-        switch (moc.variant) {
-        // experiments (moc_kernel_pipe.cuh): both feeds are parity-green and slower than the register-staged kernel --
-        // K1 is co-bound by issue slots (a DFMA takes two), and the staging adds instructions
-        case 10: return moc_launch_pipe<NB, 4, 3, 2>(p, st);         // cp.async ring, 16 warps / SM
-        case 23: return moc_launch_pipe<NB, 4, 2, 3, true>(p, st);   // TMA bulk-copy ring, 24 warps / SM
-        }
-    }
-    switch (moc.variant) {
-    case 1: return moc_launch_v<NB, 4, 4>(p, st);
-    case 2: return moc_launch_v<NB, 2, 4>(p, st);
-    case 3: return moc_launch_v<NB, 3, 3>(p, st);
-    case 4: return moc_launch_v<NB, 5, 2>(p, st);
-    case 5: return moc_launch_v<NB, 3, 4>(p, st);
-    }
-    return moc_launch_v<NB, 4, 3>(p, st);
+    // 4 vector pairs per lane in flight, 3 CTAs of 256 threads per SM.  The staged feeds (cp.async / TMA rings), the class
+    // formulation and the other unroll / occupancy points measured in round 1 (profiles/r01_k1_*.{txt,json}) were all
+    // slower and are no longer built; their sources are in the history (moc_kernel_{pipe,tma,class}.cuh at 028f76b).
+    return p.nrec > 1 ? moc_launch_v<NB, 4, 3, true>(p, st) : moc_launch_v<NB, 4, 3, false>(p, st);
 }
 
-
-// Class tables of the class-run kernel (moc_kernel_class.cuh).  cls(j,i) = index of the distinct mask tuple (0 = no
-// basin); a cell is transparent when fl32(e1v*e3m) is zero at every level.  Segment g of alignment s covers the vectors
-// [32g, 32g+32) of the flat 16-byte grid, i.e. the cells [128g - s, 128g - s + 128); positions of existing vectors that
-// fall outside the row count as non-transparent cells of class 0 (their products must not be added).
-static int moc_build_class_tables(const float *e1v, const float *e3m)
+// inputs_fresh: the record (or the area field) may have been written by work enqueued on `st` after the previous K1 launch
+// (byte swap, -vvl area build, -decomp stencil, a caller's producer kernel): no load may then precede griddepcontrol.wait.
+// nrec > 1: one launch over the records zv_list[0..nrec) -> out_list[0..nrec) (device arrays of pointers).
+static int moc_launch(const float *d_zv, double *d_out, Workspace &ws, cudaStream_t st, int noscan = 0, bool inputs_fresh = true,
+                      int nrec = 1, const float *const *zv_list = nullptr, double *const *out_list = nullptr, int *batch_col = nullptr)
 {
-    const int nx = moc.nx, ny = moc.ny, nzm1 = moc.nz - 1;
-    const size_t nxy = (size_t)nx * ny;
-    std::vector<uint8_t> transp(nxy, 1);
-    for (int k = 0; k < nzm1; ++k)
-        for (size_t c = 0; c < nxy; ++c)
-            if (transp[c]) { const float a = e1v[c] * e3m[(size_t)k * nxy + c]; if (!(a == 0.0f)) transp[c] = 0; }
-    const int nvec_max = (nx + 6) >> 2;
-    const int nseg = (nvec_max + 31) / 32;
-    moc.segpitch = ((nseg + 3) / 4) * 4 + 4;   // + one word: the kernel fetches the segment bytes one trip ahead
-    std::vector<uint8_t> seg((size_t)4 * ny * moc.segpitch, (uint8_t)0xFE);
-    for (int s = 0; s < 4; ++s) {
-        const int nvec = (s + nx + 3) >> 2;
-        for (int j = 0; j < ny; ++j) {
-            uint8_t *row = seg.data() + ((size_t)s * ny + j) * moc.segpitch;
-            for (int gsg = 0; gsg < nseg; ++gsg) {
-                int state = 0xFE;
-                for (int pos = 0; pos < 128 && state != 0xFF; ++pos) {
-                    if (32 * gsg + pos / 4 >= nvec) break;
-                    const long i = 128L * gsg - s + pos;
-                    int c;
-                    if (i < 0 || i >= nx) c = 0;
-                    else { if (transp[(size_t)j * nx + i]) continue; c = moc.h_cls[(size_t)j * nx + i]; }
-                    if (state == 0xFE) state = c;
-                    else if (state != c) state = 0xFF;
-                }
-                row[gsg] = (uint8_t)state;
-            }
-        }
-    }
-    if (!moc.d_segtab) CDF_CUDA(cudaMalloc(&moc.d_segtab, seg.size()));
-    CDF_CUDA(cudaMemcpyAsync(moc.d_segtab, seg.data(), seg.size(), cudaMemcpyHostToDevice, g.s_compute));
-    CDF_CUDA(cudaStreamSynchronize(g.s_compute));
-    return CDFGPU_OK;
-}
-
-// classes + one-hot class words; returns with moc.use_class = false when the class formulation does not apply
-static int moc_setup_classes(const float *e1v, const float *e3m, const int16_t *ibmask)
-{
-    const int nx = moc.nx, ny = moc.ny, nb = moc.nb;
-    const size_t nxy = (size_t)nx * ny;
-    moc.use_class = false;
-    {   // experiment, off by default: parity-green but slower than the basin kernel (see moc_kernel_class.cuh)
-        const char *e = getenv("CDFGPU_K1");
-        if (!e || strcmp(e, "class")) return CDFGPU_OK;
-    }
-    uint32_t bits_of[kMocMaxClasses + 1] = {0};
-    int nclass = 1;
-    moc.h_cls.assign(nxy, 0);
-    for (size_t c = 0; c < nxy; ++c) {
-        uint32_t bits = 0;
-        for (int b = 0; b < nb; ++b) if (ibmask[c * nb + b]) bits |= 1u << b;
-        int qn = 0;
-        while (qn < nclass && bits_of[qn] != bits) ++qn;
-        if (qn == nclass) {
-            if (nclass == kMocMaxClasses + 1) return CDFGPU_OK;   // too many distinct mask tuples: basin kernel
-            bits_of[nclass++] = bits;
-        }
-        moc.h_cls[c] = (uint8_t)qn;
-    }
-    if (nclass < 2) return CDFGPU_OK;   // all-zero masks: nothing to gain
-    moc.k1_nclass = nclass - 1;
-    // one-hot class bytes in the 4 pre-shifted word planes (same layout as the basin-bit planes)
-    std::vector<uint32_t> words((size_t)4 * ny * moc.pitchw, 0u);
-    for (int s = 0; s < 4; ++s)
-        for (int j = 0; j < ny; ++j) {
-            uint32_t *row = words.data() + ((size_t)s * ny + j) * moc.pitchw;
-            const uint8_t *crow = moc.h_cls.data() + (size_t)j * nx;
-            for (int w = 0; w < moc.pitchw; ++w) {
-                uint32_t x = 0;
-                for (int c = 0; c < 4; ++c) {
-                    const long i = 4L * w - s + c;
-                    if (i >= 0 && i < nx && crow[i]) x |= (1u << (crow[i] - 1)) << (8 * c);
-                }
-                row[w] = x;
-            }
-        }
-    CDF_CUDA(cudaMalloc(&moc.d_classw, words.size() * sizeof(uint32_t)));
-    CDF_CUDA(cudaMemcpyAsync(moc.d_classw, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, g.s_compute));
-    uint32_t cb[kMocMaxClasses] = {0};
-    for (int qn = 1; qn < nclass; ++qn) cb[qn - 1] = bits_of[qn];
-    CDF_CUDA(cudaMemcpyToSymbolAsync(c_k1_class_bits, cb, sizeof(cb), 0, cudaMemcpyHostToDevice, g.s_compute));
-    CDF_CUDA(cudaStreamSynchronize(g.s_compute));
-    int rc = moc_build_class_tables(e1v, e3m);
-    if (rc) return rc;
-    moc.use_class = true;
-    moc.class_grid = 0;
-    return CDFGPU_OK;
-}
-
-template <int NC>
-static int moc_class_launch_t(const MocClassParams &q, cudaStream_t st)
-{
-    auto kern = moc_zonal_class_kernel<NC, 3>;
-    if (moc.class_grid == 0) {
-        int occ = 0;
-        CDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kMocThreads, 0));
-        if (occ < 1) return set_error(CDFGPU_ERR_ARG, "cdfmoc: class kernel does not fit");
-        moc.class_grid = occ * g.sm_count;
-    }
-    kern<<<moc.class_grid, kMocThreads, 0, st>>>(q);
-    CDF_CUDA(cudaGetLastError());
-    ++g.launches;
-    return CDFGPU_OK;
-}
-
-static int moc_launch(const float *d_zv, double *d_out, Workspace &ws, cudaStream_t st, int noscan = 0)
-{
-    if (!noscan && !moc.general && moc.nclass > 0 && moc.use_tma && !moc.decomp) {  // TMA-fed class-sum kernel (experiment; not with -decomp)
-        MocTmaParams t;
-        t.zv = d_zv; t.area = moc.d_area; t.classes = moc.d_classes; t.ibmask = moc.d_ibmask; t.out = d_out;
-        t.tickets = ws.d_tickets + 3 * kTicketShards * kTicketStride;   // its own ticket pair, apart from the three sets of the default kernel
-        t.col_done = ws.d_col;
-        t.nx = moc.nx; t.ny = moc.ny; t.nz = moc.nz; t.nclass = moc.nclass;
-        t.lane_cells = moc.lane_cells; t.ntile = moc.ntile; t.cpitch = moc.cpitch;
-        t.parity = ws.parity; t.chunk = moc.tma_chunk; t.warps = moc.tma_warps;
-        ws.parity ^= 1;
-        switch (moc.nb) {
-        case 1: return moc_tma_launch_t<1>(t, st);
-        case 2: return moc_tma_launch_t<2>(t, st);
-        case 3: return moc_tma_launch_t<3>(t, st);
-        case 4: return moc_tma_launch_t<4>(t, st);
-        case 5: return moc_tma_launch_t<5>(t, st);
-        case 6: return moc_tma_launch_t<6>(t, st);
-        case 7: return moc_tma_launch_t<7>(t, st);
-        case 8: return moc_tma_launch_t<8>(t, st);
-        }
-        return set_error(CDFGPU_ERR_ARG, "cdfmoc: nb must be 1..8");
-    }
     MocParams p;
     p.zv = d_zv;
     p.area = moc.d_area;
@@ -440,30 +225,20 @@ static int moc_launch(const float *d_zv, double *d_out, Workspace &ws, cudaStrea
     p.ibmask = moc.d_ibmask;
     p.out = d_out;
     p.tickets = ws.d_tickets;
-    p.col_done = ws.d_col;
+    p.col_done = batch_col ? batch_col : ws.d_col;
     p.nx = moc.nx; p.ny = moc.ny; p.nz = moc.nz; p.pitchw = moc.pitchw;
     p.parity = ws.gen3;
     ws.gen3 = (ws.gen3 + 1) % 3;
     p.pdl = 0;
+    p.pdl_early = inputs_fresh ? 0 : 1;
     p.chunk = moc.chunk;
     p.jsplit = moc.jsplit;
     p.general = moc.general;
     p.noscan = noscan;
+    p.nrec = nrec;
+    p.zv_list = zv_list;
+    p.out_list = out_list;
     ws.parity ^= 1;
-    if (moc.use_class && !moc.general && moc.variant == 0) {   // class-run kernel (moc_kernel_class.cuh)
-        MocClassParams q;
-        q.m = p; q.classw = moc.d_classw; q.segtab = moc.d_segtab; q.segpitch = moc.segpitch; q.nb = moc.nb;
-        switch (moc.k1_nclass) {
-        case 1: return moc_class_launch_t<1>(q, st);
-        case 2: return moc_class_launch_t<2>(q, st);
-        case 3: return moc_class_launch_t<3>(q, st);
-        case 4: return moc_class_launch_t<4>(q, st);
-        case 5: return moc_class_launch_t<5>(q, st);
-        case 6: return moc_class_launch_t<6>(q, st);
-        case 7: return moc_class_launch_t<7>(q, st);
-        case 8: return moc_class_launch_t<8>(q, st);
-        }
-    }
     switch (moc.nb) {
     case 1: return moc_launch_t<1>(p, st);
     case 2: return moc_launch_t<2>(p, st);
@@ -716,7 +491,8 @@ int cdfmoc_gpu_teardown(void)
     if (!moc.ready && !moc.d_area) return CDFGPU_OK;
     if (g.inited) cdfgpu_synchronize();
     cudaFree(moc.d_e1v); cudaFree(moc.d_e3m); cudaFree(moc.d_area); cudaFree(moc.d_maskw);
-    cudaFree(moc.d_ibmask); cudaFree(moc.d_flag); cudaFree(moc.d_classes); cudaFree(moc.d_ext); cudaFree(moc.d_classw); cudaFree(moc.d_segtab);
+    cudaFree(moc.d_ibmask); cudaFree(moc.d_flag); cudaFree(moc.d_ext);
+    cudaFree(moc.d_batch_zv); cudaFree(moc.d_batch_out); cudaFree(moc.d_batch_col);
     cudaFree(moc.d_e1u); cudaFree(moc.d_zcoef); cudaFree(moc.d_zt); cudaFree(moc.d_zs); cudaFree(moc.d_sig);
     cudaFree(moc.d_hdep); cudaFree(moc.d_zvgeo); cudaFree(moc.d_umask); cudaFree(moc.d_tmask); cudaFree(moc.d_dvbt);
     cudaFree(moc.d_dvgeo); cudaFree(moc.d_sh); cudaFree(moc.d_bt); cudaFree(moc.d_ag); cudaFree(moc.d_btw);
@@ -736,10 +512,6 @@ int cdfmoc_gpu_setup(int nx, int ny, int nz, int nb, const float *e1v, const flo
     moc.nx = nx; moc.ny = ny; moc.nz = nz; moc.nb = nb;
     moc.pitchw = ((nx + 6) / 4 + 1 + 3) & ~3;   // rows of the mask planes start on 16-byte boundaries (bulk copies)
     {
-        const char *e = getenv("CDFGPU_K1");
-        moc.use_tma = e && !strcmp(e, "tma");
-        const char *v = getenv("CDFGPU_K1_VARIANT");
-        moc.variant = v ? atoi(v) : 0;
         const char *d = getenv("CDFGPU_K1_PDL");
         moc.pdl = !(d && atoi(d) == 0);
     }
@@ -770,39 +542,9 @@ int cdfmoc_gpu_setup(int nx, int ny, int nz, int nb, const float *e1v, const flo
     CDF_CUDA(cudaMemcpyAsync(moc.d_e1v, e1v, nxy * sizeof(float), cudaMemcpyHostToDevice, g.s_compute));
     CDF_CUDA(cudaMemcpyAsync(moc.d_e3m, e3v, nxy * (size_t)(nz - 1) * sizeof(float), cudaMemcpyHostToDevice, g.s_compute));
     if ((rc = moc_build_area())) return rc;
-    moc.h_e1v.assign(e1v, e1v + nxy);
-    if (binary && (rc = moc_setup_classes(e1v, e3v, ibmask))) return rc;
     moc.smem = (size_t)(kMocThreads / 32) * (nz - 1) * nb * sizeof(double);
     moc.grid = 0;
-    // ---- TMA path geometry: tiles of 32*L cells, L = 4 (mod 8) <= 60, ntile tiles per row
-    {
-        const int cells = nx + 3;  // worst-case shifted row length
-        moc.ntile = (cells + 32 * kTmaMaxLaneCells - 1) / (32 * kTmaMaxLaneCells);
-        int L = ((cells + moc.ntile - 1) / moc.ntile + 31) / 32;
-        L = ((L + 3) / 8) * 8 + 4;
-        if (L - 8 >= 4 && 32 * (L - 8) * moc.ntile >= cells) L -= 8;
-        moc.lane_cells = L;
-        moc.cpitch = moc.ntile * 32 * L;
-        uint32_t class_bits[kTmaMaxClasses] = {0};
-        std::vector<uint8_t> planes;
-        moc.nclass = (binary && moc.use_tma) ? pack_classes(nx, ny, nb, ibmask, moc.cpitch, planes, class_bits) : 0;
-        const size_t per_warp = ((size_t)kTmaStages * 32 * L * 9 + (size_t)kTmaMaxClasses * 32 * 8 +
-                                 (size_t)(nz - 1) * nb * 8 + 64 + 127) & ~(size_t)127;
-        moc.tma_warps = (int)std::min<size_t>(8, (220 * 1024) / per_warp);
-        if (moc.tma_warps < 1) moc.nclass = 0;  // nz*nb too large for the per-warp scan buffer: register kernel
-        if (moc.nclass > 0) {
-            moc.tma_smem = per_warp * moc.tma_warps;
-            moc.tma_grid = 0;
-            const long warps_total = (long)g.sm_count * moc.tma_warps;
-            long chunk = ((long)ny * (nz - 1)) / (warps_total * 20);
-            moc.tma_chunk = (int)std::max<long>(1, std::min<long>(chunk, 8));
-            CDF_CUDA(cudaMalloc(&moc.d_classes, planes.size() + 16));
-            CDF_CUDA(cudaMemcpyAsync(moc.d_classes, planes.data(), planes.size(), cudaMemcpyHostToDevice, g.s_compute));
-            CDF_CUDA(cudaMemcpyToSymbolAsync(c_class_bits, class_bits, sizeof(class_bits), 0, cudaMemcpyHostToDevice,
-                                             g.s_compute));
-            CDF_CUDA(cudaStreamSynchronize(g.s_compute));
-        }
-    }
+    moc.grid_batch = 0;
     for (int s = 0; s < g.nslots; ++s) {
         if ((rc = make_slot_events(moc.slots[s]))) return rc;
         CDF_CUDA(cudaMalloc(&moc.slots[s].d_in[0], moc.in_elems() * sizeof(float) + 16));
@@ -821,13 +563,7 @@ int cdfmoc_gpu_set_e3v(const float *e3v)
     // the area field is read by every kernel in flight: drain first (rare path, once per record with -vvl)
     CDF_CUDA(cudaStreamSynchronize(g.s_compute));
     CDF_CUDA(cudaMemcpyAsync(moc.d_e3m, e3v, (size_t)moc.nx * moc.ny * (moc.nz - 1) * sizeof(float), cudaMemcpyHostToDevice, g.s_compute));
-    int rc = moc_build_area();
-    if (rc) return rc;
-    if (moc.use_class) {   // which cells are transparent (zero area at every level) may have changed with e3v
-        moc.h_e1v.resize((size_t)moc.nx * moc.ny);
-        rc = moc_build_class_tables(moc.h_e1v.data(), e3v);
-    }
-    return rc;
+    return moc_build_area();
 }
 
 int cdfmoc_gpu_submit(int slot, int jt, const float *zv)
@@ -844,7 +580,8 @@ int cdfmoc_gpu_submit(int slot, int jt, const float *zv)
     int rc = swap_record(s.d_in[0], moc.in_elems(), g.s_compute);
     if (rc) return rc;
     CDF_CUDA(cudaEventRecord(s.ev_k0, g.s_compute));
-    rc = moc_launch(s.d_in[0], s.d_out, moc.ws_int, g.s_compute);
+    // the H2D copy is ordered by the event above; a byte swap on this stream writes the record right before K1
+    rc = moc_launch(s.d_in[0], s.d_out, moc.ws_int, g.s_compute, 0, g.big_endian_input);
     if (rc) return rc;
     CDF_CUDA(cudaEventRecord(s.ev_k1, g.s_compute));
     s.used = true;
@@ -871,8 +608,46 @@ int cdfmoc_gpu_compute_device(const float *d_zv, double *d_dmoc, void *stream)
     REQUIRE_INIT();
     REQUIRE(moc.ready, CDFGPU_ERR_STATE, "cdfmoc_gpu_compute_device: cdfmoc_gpu_setup has not been called");
     REQUIRE(d_zv && d_dmoc, CDFGPU_ERR_ARG, "cdfmoc_gpu_compute_device: null pointer");
-    if (stream == nullptr) return moc_launch(d_zv, d_dmoc, moc.ws_int, g.s_compute);
-    return moc_launch(d_zv, d_dmoc, moc.ws_ext, (cudaStream_t)stream);
+    // on the library's own stream the caller must have synchronised its producers; on a caller stream the record may come
+    // from the kernel right before this one unless the caller said otherwise (cdfgpu_set_device_inputs_ready)
+    if (stream == nullptr) return moc_launch(d_zv, d_dmoc, moc.ws_int, g.s_compute, 0, false);
+    return moc_launch(d_zv, d_dmoc, moc.ws_ext, (cudaStream_t)stream, 0, !g.device_inputs_ready);
+}
+
+// One launch over nrec device-resident records: the work units run over (record, row, levels), so the launch overhead and
+// the ramp-up / tail of the persistent grid are paid once per batch instead of once per record.
+int cdfmoc_gpu_compute_device_batch(const float *const *d_zv, double *const *d_dmoc, int nrec, void *stream)
+{
+    REQUIRE_INIT();
+    REQUIRE(moc.ready, CDFGPU_ERR_STATE, "cdfmoc_gpu_compute_device_batch: cdfmoc_gpu_setup has not been called");
+    REQUIRE(d_zv && d_dmoc && nrec >= 1, CDFGPU_ERR_ARG, "cdfmoc_gpu_compute_device_batch: bad argument");
+    {
+        const double units = (double)nrec * moc.ny * (moc.nz - 1);
+        REQUIRE(units < 2.0e9, CDFGPU_ERR_ARG, "cdfmoc_gpu_compute_device_batch: too many work units for one launch");
+    }
+    for (int r = 0; r < nrec; ++r) REQUIRE(d_zv[r] && d_dmoc[r], CDFGPU_ERR_ARG, "cdfmoc_gpu_compute_device_batch: null pointer");
+    cudaStream_t st = stream ? (cudaStream_t)stream : g.s_compute;
+    if (nrec == 1) return cdfmoc_gpu_compute_device(d_zv[0], d_dmoc[0], stream);
+    if (nrec > moc.batch_cap) {
+        CDF_CUDA(cudaDeviceSynchronize());   // (re)allocation of the pointer tables: rare, and no launch may still read them
+        cudaFree(moc.d_batch_zv); cudaFree(moc.d_batch_out); cudaFree(moc.d_batch_col);
+        moc.d_batch_zv = nullptr; moc.d_batch_out = nullptr; moc.d_batch_col = nullptr;
+        moc.batch_cap = 0;
+        CDF_CUDA(cudaMalloc(&moc.d_batch_zv, (size_t)2 * nrec * sizeof(float *)));    // two tables in rotation: the copy for launch
+        CDF_CUDA(cudaMalloc(&moc.d_batch_out, (size_t)2 * nrec * sizeof(double *)));  // N+1 must not overwrite launch N's
+        CDF_CUDA(cudaMalloc(&moc.d_batch_col, (size_t)nrec * moc.ny * sizeof(int)));
+        CDF_CUDA(cudaMemsetAsync(moc.d_batch_col, 0, (size_t)nrec * moc.ny * sizeof(int), st));
+        moc.batch_cap = nrec;
+        moc.batch_flip = 0;
+    }
+    // stream-ordered copies of the pointer tables (pageable source: the runtime stages them before returning)
+    const float **tz = moc.d_batch_zv + (size_t)moc.batch_flip * moc.batch_cap;
+    double **to = moc.d_batch_out + (size_t)moc.batch_flip * moc.batch_cap;
+    moc.batch_flip ^= 1;
+    CDF_CUDA(cudaMemcpyAsync(tz, d_zv, (size_t)nrec * sizeof(float *), cudaMemcpyHostToDevice, st));
+    CDF_CUDA(cudaMemcpyAsync(to, d_dmoc, (size_t)nrec * sizeof(double *), cudaMemcpyHostToDevice, st));
+    // the pointer tables are written on this stream right before the kernel: no load ahead of the predecessor
+    return moc_launch(d_zv[0], d_dmoc[0], stream ? moc.ws_ext : moc.ws_int, st, 0, true, nrec, tz, to, moc.d_batch_col);
 }
 
 int cdfmoc_gpu_maxmoc(int slot, int basin, int ijmin, int ijmax, int ikmin, int ikmax, float *ovt, int *loc)

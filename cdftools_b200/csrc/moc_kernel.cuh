@@ -36,6 +36,10 @@ struct MocParams {
     int nx, ny, nz, pitchw;
     int parity;                         // launch generation mod 3 selecting tickets[parity]; this launch re-arms (parity+1)%3
     int pdl;                            // launched with programmatic stream serialization: may overlap the previous launch's tail
+    int pdl_early;                      // ... and the inputs were complete before the predecessor was launched: loads may precede the wait
+    int nrec;                           // records of this launch (1, or a batch: cdfmoc_gpu_compute_device_batch)
+    const float *const *zv_list;        // batch: [nrec] records (device array of device pointers); null for a single record
+    double *const *out_list;            // batch: [nrec] result slabs; col_done then holds nrec*ny counters
     int chunk;                          // consecutive levels of one column handed out per ticket
     int jsplit;                         // columns j >= jsplit are handed out ONE level per ticket (short tail), see kernel
     int general;                        // 1: masks are not 0/1 (or area not finite) -> literal chain everywhere
@@ -75,14 +79,14 @@ __device__ __forceinline__ void moc_cell(float a, float v, uint32_t mword, doubl
 
 // Fast path: exact for 0/1 masks and finite products.  Returns lane partial sums.
 template <int NB, int kMocUnroll>
-__device__ __forceinline__ void row_sums_fast(const MocParams &p, int j, int k, int lane, uint64_t pol,
+__device__ __forceinline__ void row_sums_fast(const MocParams &p, const float *__restrict__ zv, int j, int k, int lane, uint64_t pol,
                                               double (&acc)[NB], float &badf)
 {
     const size_t e0 = ((size_t)k * p.ny + j) * (size_t)p.nx;
     const int s = (int)(e0 & 3);
     const size_t a0 = e0 - s;
     const int nvec = (s + p.nx + 3) >> 2;
-    const float4 *__restrict__ v4 = reinterpret_cast<const float4 *>(p.zv + a0);
+    const float4 *__restrict__ v4 = reinterpret_cast<const float4 *>(zv + a0);
     const float4 *__restrict__ a4 = reinterpret_cast<const float4 *>(p.area + a0);
     const uint32_t *__restrict__ mw = p.maskw + ((size_t)s * p.ny + j) * p.pitchw;
 
@@ -115,16 +119,18 @@ __device__ __forceinline__ void row_sums_fast(const MocParams &p, int j, int k, 
 // General path: the literal chain of cdfmoc.f90:373-374 with INTEGER(2) mask values (any value, NaN/Inf safe).
 // Handles the whole row (sums, warp reduction, store of the raw sums) so that the fast path keeps its
 // accumulators in registers.
-template <int NB>
-__device__ __noinline__ void row_general_store(const MocParams &p, int j, int k, int lane)
+template <int NB, bool BATCH>
+__device__ __noinline__ void row_general_store(const MocParams &p, int rec, int j, int k, int lane)
 {
+    const float *__restrict__ zv = BATCH ? p.zv_list[rec] : p.zv;
+    double *__restrict__ out = BATCH ? p.out_list[rec] : p.out;
     const size_t e0 = ((size_t)k * p.ny + j) * (size_t)p.nx;
     double acc[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) acc[b] = 0.0;
     for (int i = lane; i < p.nx; i += kWarp) {
         const float a = p.area[e0 + i];
-        const float v = p.zv[e0 + i];
+        const float v = zv[e0 + i];
         const int16_t *m = p.ibmask + ((size_t)j * p.nx + i) * NB;
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
@@ -135,11 +141,14 @@ __device__ __noinline__ void row_general_store(const MocParams &p, int j, int k,
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const double t = warp_sum(acc[b]);
-        if (lane == b) p.out[((size_t)k * p.ny + j) * NB + b] = t;
+        if (lane == b) out[((size_t)k * p.ny + j) * NB + b] = t;
     }
 }
 
-template <int NB, int UNROLL, int MINB>
+// BATCH: the launch runs over several records (MocParams::nrec, zv_list, out_list); a compile-time switch, because the
+// single-record kernel sits at its register budget (80 of 85 for 3 CTAs per SM) and takes p.zv / p.out / p.col_done
+// straight from the constant bank.
+template <int NB, int UNROLL, int MINB, bool BATCH>
 __global__ void __launch_bounds__(kMocThreads, MINB) moc_zonal_scan_kernel(const MocParams p)
 {
     extern __shared__ double s_scan[];  // [warps][(nz-1)*NB]
@@ -158,19 +167,24 @@ __global__ void __launch_bounds__(kMocThreads, MINB) moc_zonal_scan_kernel(const
     const int chunks_per_col = (nzm1 + p.chunk - 1) / p.chunk;
     const int jsplit = min(max(p.jsplit, 0), p.ny);
     const int nbig = jsplit * chunks_per_col;
-    const int nunits = nbig + (p.ny - jsplit) * nzm1;
+    const int nunits_rec = nbig + (p.ny - jsplit) * nzm1;   // units of one record
+    const int nunits = BATCH ? nunits_rec * p.nrec : nunits_rec;   // a batch launch runs over (record, unit)
     int *tickets = p.tickets + p.parity * (kTicketShards * kTicketStride);
     {   // re-arm the next launch's counters (three sets in rotation: with programmatic dependent launch the next launch
         // starts while this one drains, and IT re-arms the set after its own -- never the one still in use here)
         int *other = p.tickets + ((p.parity + 1) % 3) * (kTicketShards * kTicketStride);
+        // When the record (or the area field) may have been written by the predecessor itself -- byte swap, -vvl area build,
+        // -decomp stencil, a caller's kernel right in front -- the host clears pdl_early and every CTA waits before its
+        // first load: only stores are guaranteed invisible until griddepcontrol.wait, loads are not.
+        if (p.pdl && (blockIdx.x == 0 || !p.pdl_early)) asm volatile("griddepcontrol.wait;" ::: "memory");
         if (blockIdx.x == 0) {
             // under PDL the set to re-arm may still be in use two launches back if CTAs of the launch in between retired
             // without work: block 0 re-arms (and only then releases the next launch) once its predecessor is complete
-            if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
             if (threadIdx.x < kTicketShards) {
                 other[threadIdx.x * kTicketStride] = 0;
                 __threadfence();
             }
+            __syncthreads();   // every warp of block 0 releases the dependents only after the re-armed counters are visible
         }
     }
     // Programmatic dependent launch: the per-launch fixed cost of this kernel (launch gap, ramp-up, and a tail in which
@@ -182,7 +196,7 @@ __global__ void __launch_bounds__(kMocThreads, MINB) moc_zonal_scan_kernel(const
     // consecutive launches.
     const bool pdl = p.pdl != 0;
     if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    bool parked = pdl && blockIdx.x != 0;   // this warp's first unit goes to the stash (block 0 has already waited)
+    bool parked = pdl && p.pdl_early && blockIdx.x != 0;   // this warp's first unit goes to the stash (the others have waited)
     double *stash = s_scan + (size_t)warp * nzm1 * NB;
     int shard = (blockIdx.x * (kMocThreads / 32) + warp) % kTicketShards;
     auto take = [&](int sh) {   // lane 0: unit index from shard sh (may be >= nunits when the shard is dry)
@@ -213,12 +227,23 @@ __global__ void __launch_bounds__(kMocThreads, MINB) moc_zonal_scan_kernel(const
         int unext = 0;
         if (lane == 0) unext = take(shard);  // request the next unit now; its latency hides behind the rows below
         int j, k0, k1;
-        if (u < nbig) {
-            j = u / chunks_per_col;
-            k0 = (u - j * chunks_per_col) * p.chunk;
+        const float *__restrict__ zv = p.zv;
+        double *__restrict__ out = p.out;
+        int *col_done = p.col_done;
+        int ur = u, rec = 0;
+        if (BATCH) {   // the record of this unit
+            rec = u / nunits_rec;
+            ur = u - rec * nunits_rec;
+            zv = p.zv_list[rec];
+            out = p.out_list[rec];
+            col_done += (size_t)rec * p.ny;
+        }
+        if (ur < nbig) {
+            j = ur / chunks_per_col;
+            k0 = (ur - j * chunks_per_col) * p.chunk;
             k1 = min(k0 + p.chunk, nzm1);
         } else {
-            const int u2 = u - nbig;
+            const int u2 = ur - nbig;
             const int dj = u2 / nzm1;
             j = jsplit + dj;
             k0 = u2 - dj * nzm1;
@@ -231,7 +256,7 @@ __global__ void __launch_bounds__(kMocThreads, MINB) moc_zonal_scan_kernel(const
             bool bad = p.general != 0;
             if (!bad) {
                 float badf = 0.0f;
-                row_sums_fast<NB, UNROLL>(p, j, k, lane, pol, acc, badf);
+                row_sums_fast<NB, UNROLL>(p, zv, j, k, lane, pol, acc, badf);
                 bad = __any_sync(kFull, badf != badf);
             }
             if (bad) {
@@ -239,17 +264,17 @@ __global__ void __launch_bounds__(kMocThreads, MINB) moc_zonal_scan_kernel(const
                     asm volatile("griddepcontrol.wait;" ::: "memory");
                     __syncwarp();
                     for (int kk = k0; kk < k; ++kk)
-                        if (lane < NB) p.out[((size_t)kk * p.ny + j) * NB + lane] = stash[(kk - k0) * NB + lane];
+                        if (lane < NB) out[((size_t)kk * p.ny + j) * NB + lane] = stash[(kk - k0) * NB + lane];
                     parked = false;
                 }
-                row_general_store<NB>(p, j, k, lane);
+                row_general_store<NB, BATCH>(p, rec, j, k, lane);
             } else {
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
                     const double t = warp_sum(acc[b]);
                     if (lane == b) {
                         if (parked) stash[(k - k0) * NB + b] = t;
-                        else p.out[((size_t)k * p.ny + j) * NB + b] = t;
+                        else out[((size_t)k * p.ny + j) * NB + b] = t;
                     }
                 }
             }
@@ -258,7 +283,7 @@ __global__ void __launch_bounds__(kMocThreads, MINB) moc_zonal_scan_kernel(const
             asm volatile("griddepcontrol.wait;" ::: "memory");
             __syncwarp();
             for (int kk = k0; kk < k1; ++kk)
-                if (lane < NB) p.out[((size_t)kk * p.ny + j) * NB + lane] = stash[(kk - k0) * NB + lane];
+                if (lane < NB) out[((size_t)kk * p.ny + j) * NB + lane] = stash[(kk - k0) * NB + lane];
             parked = false;
         }
         // publish the rows, then count them; the warp that completes column j integrates it vertically.
@@ -269,29 +294,29 @@ __global__ void __launch_bounds__(kMocThreads, MINB) moc_zonal_scan_kernel(const
         if (lane == 0) {
             int old;
             asm volatile("atom.add.release.gpu.global.s32 %0, [%1], %2;"
-                         : "=r"(old) : "l"(p.col_done + j), "r"(k1 - k0) : "memory");
+                         : "=r"(old) : "l"(col_done + j), "r"(k1 - k0) : "memory");
             done = old + (k1 - k0);
         }
         done = __shfl_sync(kFull, done, 0);
         if (done == nzm1 && p.noscan) {
-            if (lane == 0) p.col_done[j] = 0;
+            if (lane == 0) col_done[j] = 0;
         } else if (done == nzm1) {
             asm volatile("fence.acq_rel.gpu;" ::: "memory");
             double *sc = s_scan + (size_t)warp * nzm1 * NB;
             for (int t = lane; t < nzm1 * NB; t += kWarp) {
                 const int kk = t / NB, b = t - kk * NB;
-                sc[t] = __ldcg(p.out + ((size_t)kk * p.ny + j) * NB + b) / 1.0e6;  // dmoc(:,jj,jk)/1.d6
+                sc[t] = __ldcg(out + ((size_t)kk * p.ny + j) * NB + b) / 1.0e6;  // dmoc(:,jj,jk)/1.d6
             }
             __syncwarp();
             if (lane < NB) {
                 double psi = 0.0;
-                p.out[((size_t)nzm1 * p.ny + j) * NB + lane] = 0.0;  // dmoc(:,:,npk) stays 0
+                out[((size_t)nzm1 * p.ny + j) * NB + lane] = 0.0;  // dmoc(:,:,npk) stays 0
                 for (int kk = nzm1 - 1; kk >= 0; --kk) {
                     psi = psi + sc[kk * NB + lane];  // dmoc(:,jj,jk+1) + dmoc(:,jj,jk)/1.d6
-                    p.out[((size_t)kk * p.ny + j) * NB + lane] = psi;
+                    out[((size_t)kk * p.ny + j) * NB + lane] = psi;
                 }
             }
-            if (lane == 0) p.col_done[j] = 0;  // self-reset for the next launch
+            if (lane == 0) col_done[j] = 0;  // self-reset for the next launch
             __syncwarp();
         }
         u = __shfl_sync(kFull, unext, 0);

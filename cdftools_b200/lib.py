@@ -41,6 +41,7 @@ SIGNATURES = {
     "cdfmoc_gpu_submit": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
     "cdfmoc_gpu_fetch": (C.c_int, [C.c_int, C.c_void_p]),
     "cdfmoc_gpu_compute_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cdfmoc_gpu_compute_device_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "cdfmoc_gpu_kernel_ms": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
     "cdfmoc_gpu_maxmoc": (C.c_int, [C.c_int] * 6 + [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "cdfmoc_gpu_decomp_setup": (C.c_int, [C.c_int] + [C.c_void_p] * 5),
@@ -201,6 +202,16 @@ def cdfmoc_fetch(slot: int, out):
 def cdfmoc_compute_device(d_zv, d_dmoc, stream=None):
     _chk(load().cdfmoc_gpu_compute_device(_ptr(d_zv), _ptr(d_dmoc), C.c_void_p(stream_handle(stream))),
          "cdfmoc_gpu_compute_device")
+
+
+def cdfmoc_compute_device_batch(d_zv_list, d_dmoc_list, stream=None):
+    """One K1 launch over several device-resident records (lists of torch tensors / device addresses)."""
+    n = len(d_zv_list)
+    assert n == len(d_dmoc_list) and n >= 1
+    addr = lambda a: a.data_ptr() if hasattr(a, "data_ptr") else int(a)
+    zv = (C.c_void_p * n)(*[addr(a) for a in d_zv_list])
+    out = (C.c_void_p * n)(*[addr(a) for a in d_dmoc_list])
+    _chk(load().cdfmoc_gpu_compute_device_batch(zv, out, n, C.c_void_p(stream_handle(stream))), "cdfmoc_gpu_compute_device_batch")
 
 
 def cdfmoc_kernel_ms(slot: int) -> float:

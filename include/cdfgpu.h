@@ -104,6 +104,9 @@ int cdfmoc_gpu_set_e3v(const float *e3v);
 int cdfmoc_gpu_submit(int slot, int jt, const float *zv);
 int cdfmoc_gpu_fetch(int slot, double *dmoc);
 int cdfmoc_gpu_compute_device(const float *d_zv, double *d_dmoc, void *stream);
+/* The same over nrec device-resident records in ONE launch (d_zv, d_dmoc: HOST arrays of nrec device pointers): the
+ * work units run over (record, row, levels), so launch overhead, ramp-up and tail are paid once per batch. */
+int cdfmoc_gpu_compute_device_batch(const float *const *d_zv, double *const *d_dmoc, int nrec, void *stream);
 int cdfmoc_gpu_kernel_ms(int slot, float *ms); /* device time of the slot's last kernel, CUDA events */
 /* Optional epilogue on the slot's streamfunction slab: the window extrema cdfmaxmoc computes from moc.nc
  * (src/cdfmaxmoc.f90:158-167).  Values are taken as REAL(4) (what the file holds); window bounds are 1-based

@@ -61,7 +61,7 @@ def test_fortran_module_binds_the_host_facing_abi():
     include/cdfgpu.h that a Fortran host can use; the exceptions take DEVICE pointers or are C-string helpers."""
     fortran = (ROOT / "cdftools_b200" / "fortran" / "cdfgpu_mod.f90").read_text()
     bound = set(re.findall(r"NAME='(\w+)'", fortran))
-    device_side_or_c_only = {"cdfmoc_gpu_compute_device", "cdfmocsig_gpu_compute_device", "cdfmocsig_gpu_bins_device",
+    device_side_or_c_only = {"cdfmoc_gpu_compute_device", "cdfmoc_gpu_compute_device_batch", "cdfmocsig_gpu_compute_device", "cdfmocsig_gpu_bins_device",
                              "cdfmocsig_gpu_bins_device_stats", "cdfgpu_set_device_inputs_ready", "cdfgpu_microbench", "cdfgpu_h2d_probe",
                              "cdfgpu_strerror", "cdfgpu_launch_count"}
     declared = _declared()
