@@ -27,8 +27,17 @@ struct Ctx {
     unsigned long long launches = 0;
     bool big_endian_input = false;
     bool device_inputs_ready = false;   // cdfgpu_set_device_inputs_ready
+    // latitude-band sharding (api_multi.inc): the host arrays of the current call are bands of larger arrays
+    size_t host_level_stride = 0;       // elements between consecutive levels of the host record (0: contiguous)
+    size_t host_out_pitch = 0;          // cdfmoc result: elements between consecutive levels of the host slab (0: contiguous)
 };
-static Ctx g;
+constexpr int kMaxDev = 8;
+static Ctx g_dev[kMaxDev];
+static int g_cur = 0;      // device the single-device code below works on (the ABI is single-threaded)
+static int g_ndev = 1;     // devices this process drives (cdfgpu_init: $CDFGPU_DEVICES)
+static int g_shard = 0;    // 0: records go round-robin over the devices; 1: every record is split into latitude bands
+static bool g_defer_sync = false;   // band gather: the per-device fetches are enqueued first and awaited together
+#define g (g_dev[g_cur])
 
 struct Workspace {  // scheduling counters of one stream-ordered sequence of launches
     int *d_tickets = nullptr;  // [3] sets of sharded counters (K1: three in rotation; the other kernels use the first two)
@@ -47,8 +56,9 @@ struct Slot {
 
 // The polynomial-EOS coefficient table lives in one __constant__ symbol shared by cdfmocsig and cdfmoc -decomp; it is
 // (re)loaded, stream-ordered, whenever the launching plan wants the other coefficient set.
-static int g_eos_loaded = -1;   // -1 none, 0 EOS80, 1 TEOS10
+static int g_eos_loaded_dev[kMaxDev] = {-1, -1, -1, -1, -1, -1, -1, -1};   // -1 none, 0 EOS80, 1 TEOS10 (per device)
 static EosConst g_eos_host;
+#define g_eos_loaded (g_eos_loaded_dev[g_cur])
 static int ensure_eos(int teos10, cudaStream_t st)
 {
     if (g_eos_loaded == teos10) return CDFGPU_OK;
@@ -61,6 +71,18 @@ static int ensure_eos(int teos10, cudaStream_t st)
     CDF_CUDA(cudaMemcpyToSymbolAsync(c_eos, &g_eos_host, sizeof(g_eos_host), 0, cudaMemcpyHostToDevice, st));
     CDF_CUDA(cudaStreamSynchronize(st));
     g_eos_loaded = teos10;
+    return CDFGPU_OK;
+}
+
+// host record (nlev levels of level_elems values) -> device: contiguous, or one band of a larger array per level
+static int h2d_record(float *dst, const float *src, size_t nlev, size_t level_elems, cudaStream_t st)
+{
+    if (g.host_level_stride == 0 || g.host_level_stride == level_elems) {
+        CDF_CUDA(cudaMemcpyAsync(dst, src, nlev * level_elems * sizeof(float), cudaMemcpyHostToDevice, st));
+    } else {
+        CDF_CUDA(cudaMemcpy2DAsync(dst, level_elems * sizeof(float), src, g.host_level_stride * sizeof(float), level_elems * sizeof(float),
+                                   nlev, cudaMemcpyHostToDevice, st));
+    }
     return CDFGPU_OK;
 }
 
@@ -168,7 +190,8 @@ struct MocPlan {
     size_t in_elems() const { return (size_t)(nz - 1) * ny * nx; }
     size_t out_elems() const { return (size_t)nz * ny * nb; }
 };
-static MocPlan moc;
+static MocPlan moc_dev[kMaxDev];
+#define moc (moc_dev[g_cur])
 
 template <int NB, int UNROLL, int MINB, bool BATCH>
 static int moc_launch_v(const MocParams &p, cudaStream_t st)
@@ -297,8 +320,19 @@ using namespace cdfgpu;
     if (!g.inited) return set_error(CDFGPU_ERR_STATE, "cdfgpu_init has not been called")
 #define REQUIRE(cond, code, msg)                                                                 \
     if (!(cond)) return set_error(code, msg)
+// the sibling tools (cdfzonal*, cdfmhst, cdftransig) and the probes run on the first device of the process
+#define FIRST_DEVICE()                                  \
+    do {                                                \
+        if (g_cur != 0) {                               \
+            g_cur = 0;                                  \
+            cudaSetDevice(g_dev[0].device);             \
+        }                                               \
+    } while (0)
 
 extern "C" {
+static int cdfmoc_gpu_teardown_dev(void);
+static int cdfmocsig_gpu_teardown_dev(void);
+static int cdfmocsig_gpu_bins_device_stats_dev(const float *d_zt, const float *d_zs, int32_t *d_ibin, unsigned long long *stats3, void *stream);
 
 int cdfgpu_abi_version(void) { return 1; }
 
@@ -328,7 +362,7 @@ int cdfgpu_device_count(void)
     return n;
 }
 
-int cdfgpu_init(int device, int nslots)
+static int cdfgpu_init_dev(int device, int nslots)
 {
     if (g.inited) return CDFGPU_OK;
     const int n = cdfgpu_device_count();
@@ -362,7 +396,7 @@ int cdfgpu_init(int device, int nslots)
     return CDFGPU_OK;
 }
 
-int cdfgpu_synchronize(void)
+static int cdfgpu_synchronize_dev(void)
 {
     REQUIRE_INIT();
     CDF_CUDA(cudaStreamSynchronize(g.s_copy));
@@ -371,26 +405,30 @@ int cdfgpu_synchronize(void)
     return CDFGPU_OK;
 }
 
-int cdfgpu_finalize(void)
+static int cdfgpu_finalize_dev(void)
 {
     if (!g.inited) return CDFGPU_OK;
-    cdfgpu_synchronize();
-    cdfmoc_gpu_teardown();
-    cdfmocsig_gpu_teardown();
-    cdfzonal_gpu_teardown();
-    cdfmhst_gpu_teardown();
-    cdftransig_gpu_teardown();
+    cdfgpu_synchronize_dev();
+    cdfmoc_gpu_teardown_dev();
+    cdfmocsig_gpu_teardown_dev();
+    if (g_cur == 0) {   // the sibling tools live on the first device
+        cdfzonal_gpu_teardown();
+        cdfmhst_gpu_teardown();
+        cdftransig_gpu_teardown();
+    }
     cudaStreamDestroy(g.s_compute);
     cudaStreamDestroy(g.s_copy);
     cudaStreamDestroy(g.s_d2h);
     g = Ctx();
+    g_eos_loaded = -1;
+    cudaGetLastError();   // nothing left pending for the next session of this process
     return CDFGPU_OK;
 }
 
 void *cdfgpu_pinned_alloc(size_t nbytes)
 {
     void *p = nullptr;
-    cudaError_t e = cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocPortable);   // page-locked for every device of the process
     if (e != cudaSuccess) {
         set_error(CDFGPU_ERR_NOMEM, "cudaHostAlloc: %s", cudaGetErrorString(e));
         cudaGetLastError();
@@ -407,6 +445,7 @@ int cdfgpu_pinned_free(void *p)
 // on the library's copy stream, nothing else running.  gbs = GB/s of this process (bench.py sums the ranks).
 int cdfgpu_h2d_probe(const void *pinned, size_t nbytes, int reps, double *gbs)
 {
+    FIRST_DEVICE();
     REQUIRE_INIT();
     REQUIRE(pinned && nbytes > 0 && reps > 0 && gbs, CDFGPU_ERR_ARG, "cdfgpu_h2d_probe: bad argument");
     void *d = nullptr;
@@ -426,10 +465,15 @@ int cdfgpu_h2d_probe(const void *pinned, size_t nbytes, int reps, double *gbs)
     cudaFree(d);
     return CDFGPU_OK;
 }
-unsigned long long cdfgpu_launch_count(void) { return g.launches; }
+unsigned long long cdfgpu_launch_count(void)
+{
+    unsigned long long n = 0;
+    for (int d = 0; d < g_ndev; ++d) n += g_dev[d].launches;
+    return n;
+}
 int cdfgpu_set_input_big_endian(int on)
 {
-    g.big_endian_input = on != 0;
+    for (int d = 0; d < kMaxDev; ++d) g_dev[d].big_endian_input = on != 0;
     return CDFGPU_OK;
 }
 
@@ -438,6 +482,7 @@ int cdfgpu_set_input_big_endian(int on)
 // over the chip (CUDA events), out[2] = SM clock in MHz implied by the two.
 int cdfgpu_microbench(int kind, double *out3)
 {
+    FIRST_DEVICE();
     REQUIRE_INIT();
     REQUIRE(kind >= 0 && kind <= 4 && out3, CDFGPU_ERR_ARG, "cdfgpu_microbench: kind must be 0..4");
     const int iters = 20000, nblk = g.sm_count;
@@ -481,15 +526,15 @@ int cdfgpu_microbench(int kind, double *out3)
 
 int cdfgpu_set_device_inputs_ready(int on)
 {
-    g.device_inputs_ready = on != 0;
+    for (int d = 0; d < kMaxDev; ++d) g_dev[d].device_inputs_ready = on != 0;
     return CDFGPU_OK;
 }
 
 // --------------------------------------------------------------------------------------------------- cdfmoc
-int cdfmoc_gpu_teardown(void)
+static int cdfmoc_gpu_teardown_dev(void)
 {
     if (!moc.ready && !moc.d_area) return CDFGPU_OK;
-    if (g.inited) cdfgpu_synchronize();
+    if (g.inited) cdfgpu_synchronize_dev();
     cudaFree(moc.d_e1v); cudaFree(moc.d_e3m); cudaFree(moc.d_area); cudaFree(moc.d_maskw);
     cudaFree(moc.d_ibmask); cudaFree(moc.d_flag); cudaFree(moc.d_ext);
     cudaFree(moc.d_batch_zv); cudaFree(moc.d_batch_out); cudaFree(moc.d_batch_col);
@@ -502,13 +547,13 @@ int cdfmoc_gpu_teardown(void)
     return CDFGPU_OK;
 }
 
-int cdfmoc_gpu_setup(int nx, int ny, int nz, int nb, const float *e1v, const float *e3v, const int16_t *ibmask)
+static int cdfmoc_gpu_setup_dev(int nx, int ny, int nz, int nb, const float *e1v, const float *e3v, const int16_t *ibmask)
 {
     REQUIRE_INIT();
     REQUIRE(nx >= 1 && ny >= 1 && nz >= 2, CDFGPU_ERR_ARG, "cdfmoc_gpu_setup: need nx,ny >= 1 and nz >= 2");
     REQUIRE(nb >= 1 && nb <= CDFGPU_MAX_BASINS, CDFGPU_ERR_ARG, "cdfmoc_gpu_setup: nb must be 1..8");
     REQUIRE(e1v && e3v && ibmask, CDFGPU_ERR_ARG, "cdfmoc_gpu_setup: null pointer");
-    cdfmoc_gpu_teardown();
+    cdfmoc_gpu_teardown_dev();
     moc.nx = nx; moc.ny = ny; moc.nz = nz; moc.nb = nb;
     moc.pitchw = ((nx + 6) / 4 + 1 + 3) & ~3;   // rows of the mask planes start on 16-byte boundaries (bulk copies)
     {
@@ -555,7 +600,7 @@ int cdfmoc_gpu_setup(int nx, int ny, int nz, int nb, const float *e1v, const flo
     return CDFGPU_OK;
 }
 
-int cdfmoc_gpu_set_e3v(const float *e3v)
+static int cdfmoc_gpu_set_e3v_dev(const float *e3v)
 {
     REQUIRE_INIT();
     REQUIRE(moc.ready, CDFGPU_ERR_STATE, "cdfmoc_gpu_set_e3v: cdfmoc_gpu_setup has not been called");
@@ -566,7 +611,7 @@ int cdfmoc_gpu_set_e3v(const float *e3v)
     return moc_build_area();
 }
 
-int cdfmoc_gpu_submit(int slot, int jt, const float *zv)
+static int cdfmoc_gpu_submit_dev(int slot, int jt, const float *zv)
 {
     REQUIRE_INIT();
     REQUIRE(moc.ready, CDFGPU_ERR_STATE, "cdfmoc_gpu_submit: cdfmoc_gpu_setup has not been called");
@@ -574,7 +619,10 @@ int cdfmoc_gpu_submit(int slot, int jt, const float *zv)
     REQUIRE(zv, CDFGPU_ERR_ARG, "cdfmoc_gpu_submit: null pointer");
     Slot &s = moc.slots[slot];
     if (s.used) CDF_CUDA(cudaStreamWaitEvent(g.s_copy, s.ev_k1, 0));  // previous kernel on this slot has read d_in
-    CDF_CUDA(cudaMemcpyAsync(s.d_in[0], zv, moc.in_elems() * sizeof(float), cudaMemcpyHostToDevice, g.s_copy));
+    {
+        int rch = h2d_record(s.d_in[0], zv, (size_t)(moc.nz - 1), (size_t)moc.ny * moc.nx, g.s_copy);
+        if (rch) return rch;
+    }
     CDF_CUDA(cudaEventRecord(s.ev_h2d, g.s_copy));
     CDF_CUDA(cudaStreamWaitEvent(g.s_compute, s.ev_h2d, 0));
     int rc = swap_record(s.d_in[0], moc.in_elems(), g.s_compute);
@@ -589,7 +637,7 @@ int cdfmoc_gpu_submit(int slot, int jt, const float *zv)
     return CDFGPU_OK;
 }
 
-int cdfmoc_gpu_fetch(int slot, double *dmoc)
+static int cdfmoc_gpu_fetch_dev(int slot, double *dmoc)
 {
     REQUIRE_INIT();
     REQUIRE(moc.ready, CDFGPU_ERR_STATE, "cdfmoc_gpu_fetch: cdfmoc_gpu_setup has not been called");
@@ -598,12 +646,18 @@ int cdfmoc_gpu_fetch(int slot, double *dmoc)
     Slot &s = moc.slots[slot];
     REQUIRE(s.used, CDFGPU_ERR_STATE, "cdfmoc_gpu_fetch: nothing was submitted on this slot");
     CDF_CUDA(cudaStreamWaitEvent(g.s_d2h, s.ev_k1, 0));
-    CDF_CUDA(cudaMemcpyAsync(dmoc, s.d_out, moc.out_elems() * sizeof(double), cudaMemcpyDeviceToHost, g.s_d2h));
-    CDF_CUDA(cudaStreamSynchronize(g.s_d2h));
+    const size_t lev = (size_t)moc.ny * moc.nb;   // one level of the slab: (ny, nb)
+    if (g.host_out_pitch == 0 || g.host_out_pitch == lev) {
+        CDF_CUDA(cudaMemcpyAsync(dmoc, s.d_out, moc.out_elems() * sizeof(double), cudaMemcpyDeviceToHost, g.s_d2h));
+    } else {
+        CDF_CUDA(cudaMemcpy2DAsync(dmoc, g.host_out_pitch * sizeof(double), s.d_out, lev * sizeof(double), lev * sizeof(double),
+                                   (size_t)moc.nz, cudaMemcpyDeviceToHost, g.s_d2h));
+    }
+    if (!g_defer_sync) CDF_CUDA(cudaStreamSynchronize(g.s_d2h));
     return CDFGPU_OK;
 }
 
-int cdfmoc_gpu_compute_device(const float *d_zv, double *d_dmoc, void *stream)
+static int cdfmoc_gpu_compute_device_dev(const float *d_zv, double *d_dmoc, void *stream)
 {
     REQUIRE_INIT();
     REQUIRE(moc.ready, CDFGPU_ERR_STATE, "cdfmoc_gpu_compute_device: cdfmoc_gpu_setup has not been called");
@@ -616,7 +670,7 @@ int cdfmoc_gpu_compute_device(const float *d_zv, double *d_dmoc, void *stream)
 
 // One launch over nrec device-resident records: the work units run over (record, row, levels), so the launch overhead and
 // the ramp-up / tail of the persistent grid are paid once per batch instead of once per record.
-int cdfmoc_gpu_compute_device_batch(const float *const *d_zv, double *const *d_dmoc, int nrec, void *stream)
+static int cdfmoc_gpu_compute_device_batch_dev(const float *const *d_zv, double *const *d_dmoc, int nrec, void *stream)
 {
     REQUIRE_INIT();
     REQUIRE(moc.ready, CDFGPU_ERR_STATE, "cdfmoc_gpu_compute_device_batch: cdfmoc_gpu_setup has not been called");
@@ -627,7 +681,7 @@ int cdfmoc_gpu_compute_device_batch(const float *const *d_zv, double *const *d_d
     }
     for (int r = 0; r < nrec; ++r) REQUIRE(d_zv[r] && d_dmoc[r], CDFGPU_ERR_ARG, "cdfmoc_gpu_compute_device_batch: null pointer");
     cudaStream_t st = stream ? (cudaStream_t)stream : g.s_compute;
-    if (nrec == 1) return cdfmoc_gpu_compute_device(d_zv[0], d_dmoc[0], stream);
+    if (nrec == 1) return cdfmoc_gpu_compute_device_dev(d_zv[0], d_dmoc[0], stream);
     if (nrec > moc.batch_cap) {
         CDF_CUDA(cudaDeviceSynchronize());   // (re)allocation of the pointer tables: rare, and no launch may still read them
         cudaFree(moc.d_batch_zv); cudaFree(moc.d_batch_out); cudaFree(moc.d_batch_col);
@@ -650,7 +704,7 @@ int cdfmoc_gpu_compute_device_batch(const float *const *d_zv, double *const *d_d
     return moc_launch(d_zv[0], d_dmoc[0], stream ? moc.ws_ext : moc.ws_int, st, 0, true, nrec, tz, to, moc.d_batch_col);
 }
 
-int cdfmoc_gpu_maxmoc(int slot, int basin, int ijmin, int ijmax, int ikmin, int ikmax, float *ovt, int *loc)
+static int cdfmoc_gpu_maxmoc_dev(int slot, int basin, int ijmin, int ijmax, int ikmin, int ikmax, float *ovt, int *loc)
 {
     REQUIRE_INIT();
     REQUIRE(moc.ready, CDFGPU_ERR_STATE, "cdfmoc_gpu_maxmoc: cdfmoc_gpu_setup has not been called");
@@ -678,7 +732,7 @@ int cdfmoc_gpu_maxmoc(int slot, int basin, int ijmin, int ijmax, int ikmin, int 
     return CDFGPU_OK;
 }
 
-int cdfmoc_gpu_decomp_setup(int teos10, const float *e1u, const float *gphiv, const float *gdept, const int16_t *umask,
+static int cdfmoc_gpu_decomp_setup_dev(int teos10, const float *e1u, const float *gphiv, const float *gdept, const int16_t *umask,
                             const int16_t *tmask)
 {
     REQUIRE_INIT();
@@ -725,12 +779,12 @@ int cdfmoc_gpu_decomp_setup(int teos10, const float *e1u, const float *gphiv, co
     return CDFGPU_OK;
 }
 
-int cdfmoc_gpu_decomp_submit(int slot, int jt, const float *zv, const float *zt, const float *zs)
+static int cdfmoc_gpu_decomp_submit_dev(int slot, int jt, const float *zv, const float *zt, const float *zs)
 {
     REQUIRE_INIT();
     REQUIRE(moc.ready && moc.decomp, CDFGPU_ERR_STATE, "cdfmoc_gpu_decomp_submit: cdfmoc_gpu_decomp_setup has not been called");
     REQUIRE(zt && zs, CDFGPU_ERR_ARG, "cdfmoc_gpu_decomp_submit: null pointer");
-    int rc = cdfmoc_gpu_submit(slot, jt, zv);   // total MOC (cdfmoc.f90:352-388) into the slot's slab
+    int rc = cdfmoc_gpu_submit_dev(slot, jt, zv);   // total MOC (cdfmoc.f90:352-388) into the slot's slab
     if (rc) return rc;
     rc = ensure_eos(moc.dec_teos10, g.s_compute);
     if (rc) return rc;
@@ -773,12 +827,12 @@ int cdfmoc_gpu_decomp_submit(int slot, int jt, const float *zv, const float *zt,
     return CDFGPU_OK;
 }
 
-int cdfmoc_gpu_decomp_fetch(int slot, double *dmoc, double *dmoc_sh, double *dmoc_bt, double *dmoc_ag)
+static int cdfmoc_gpu_decomp_fetch_dev(int slot, double *dmoc, double *dmoc_sh, double *dmoc_bt, double *dmoc_ag)
 {
     REQUIRE_INIT();
     REQUIRE(moc.ready && moc.decomp, CDFGPU_ERR_STATE, "cdfmoc_gpu_decomp_fetch: cdfmoc_gpu_decomp_setup has not been called");
     REQUIRE(dmoc && dmoc_sh && dmoc_bt && dmoc_ag, CDFGPU_ERR_ARG, "cdfmoc_gpu_decomp_fetch: null pointer");
-    int rc = cdfmoc_gpu_fetch(slot, dmoc);
+    int rc = cdfmoc_gpu_fetch_dev(slot, dmoc);
     if (rc) return rc;
     const size_t nb8 = moc.out_elems() * sizeof(double);
     CDF_CUDA(cudaMemcpyAsync(dmoc_sh, moc.d_sh, nb8, cudaMemcpyDeviceToHost, g.s_d2h));
@@ -788,7 +842,7 @@ int cdfmoc_gpu_decomp_fetch(int slot, double *dmoc, double *dmoc_sh, double *dmo
     return CDFGPU_OK;
 }
 
-int cdfmoc_gpu_kernel_ms(int slot, float *ms)
+static int cdfmoc_gpu_kernel_ms_dev(int slot, float *ms)
 {
     REQUIRE_INIT();
     REQUIRE(moc.ready && slot >= 0 && slot < g.nslots && ms, CDFGPU_ERR_ARG, "cdfmoc_gpu_kernel_ms: bad argument");
@@ -804,3 +858,4 @@ int cdfmoc_gpu_kernel_ms(int slot, float *ms)
 #include "api_mocsig.inc"
 #include "api_zonal.inc"
 #include "api_transig.inc"
+#include "api_multi.inc"

@@ -11,7 +11,7 @@ using namespace cdfhost;
 
 static void usage(const Names &cn)
 {
-    printf(" usage : cdfmoc_gpu  -v V-file [-t T-file] [-s S-file] [-u U-file] [-o OUT-file] [-full] [-decomp] [-rapid] [-vvl] [-teos10]\n"
+    printf(" usage : cdfmoc_gpu  -v V-file [-t T-file] [-s S-file] [-u U-file] [-o OUT-file] [-full] [-decomp] [-rapid] [-vvl] [-teos10] [-nc4]\n"
            "      \n     PURPOSE :\n"
            "       Compute the Meridional Overturning Cell (MOC) on a B200 GPU: zonal integral of the\n"
            "       meridional transport for every basin, integrated from the bottom (Sv).\n"
@@ -24,6 +24,8 @@ int main(int argc, char **argv)
 {
     Names cn;
     if (argc == 1) { usage(cn); return 0; }   // the reference prints the usage and STOPs (cdfmoc.f90:129-209)
+    PhaseTimer tm("cdfmoc_gpu");
+    CudaWarmup warm;   // CUDA contexts come up while the mesh and mask files are read
     std::string cf_vfil, cf_tfil = "none", cf_sfil = "none", cf_ufil = "none", cf_moc = "moc.nc";
     std::string cglobal = "Partial step computation";
     bool lfull = false, ldec = false, lrap = false, lvvl = false, lteos10 = false;
@@ -40,6 +42,7 @@ int main(int argc, char **argv)
         else if (a == "-rapid") lrap = true;
         else if (a == "-vvl") lvvl = true;
         else if (a == "-teos10") lteos10 = true;
+        else if (a == "-nc4") note_nc4();   // DEV_TOOLS/tagnc4.tpl:1-13
         else { printf("  ERROR : %s : unknown option.\n", a.c_str()); stop(99); }
     }
     (void)lteos10; (void)cf_ufil;
@@ -115,8 +118,11 @@ int main(int argc, char **argv)
     OutFile out;
     out.create(cf_moc, cn.vdepthw, ny, nz, ovars, cglobal, navlat, gdepw, tim, vf);
 
+    tm.mark("mesh_mask_read");
     // ---- GPU: setup once, then the record pipeline
-    gpu_check(cdfgpu_init(-1, 3), "cdfgpu_init");
+    warm.join();
+    gpu_check(cdfgpu_init(-1, 3), "cdfgpu_init");   // $CDFGPU_DEVICES / $CDFGPU_SHARD: several devices behind the same calls
+    tm.mark("cuda_init_wait");
     gpu_check(cdfmoc_gpu_setup(nx, ny, nz, nb, e1v.data(), e3v.data(), ibmask.data()), "cdfmoc_gpu_setup");
     const int iv = vf.find_var(cn.vomecrty);
     if (iv < 0) { printf(" ERROR : %s not found in %s\n", cn.vomecrty.c_str(), cf_vfil.c_str()); stop(98); }
@@ -136,8 +142,16 @@ int main(int argc, char **argv)
         gpu_check(cdfmoc_gpu_decomp_setup(lteos10 ? 1 : 0, e1u.data(), gphiv.data(), gdept.data(), um.data(), tm.data()),
                   "cdfmoc_gpu_decomp_setup");
     }
-    Pinned buf0(n3), buf1(n3), buf2(n3);
-    float *bufs[3] = {buf0.p, buf1.p, buf2.p};
+    tm.mark("gpu_setup");
+    // record slots: 3 per device under time sharding (every device has its own pipeline), 3 otherwise; -vvl rebuilds the
+    // resident area field per record, so only one record per device is in flight
+    const int ndev = cdfgpu_num_devices();
+    const int ns = (lvvl || ldec) ? ((lvvl && !ldec) ? std::max(1, cdfgpu_nslots() / 3) : 1) : cdfgpu_nslots();
+    (void)ndev;
+    std::vector<Pinned *> pbuf;
+    for (int s = 0; s < std::max(ns, 3); ++s) pbuf.push_back(new Pinned(n3));
+    std::vector<float *> bufs;
+    for (auto p : pbuf) bufs.push_back(p->p);
     std::vector<double> dmoc((size_t)nb * ny * nz);
     std::vector<float> plane((size_t)nz * ny);
     auto drain = [&](int slot, int jt) {   // cdfmoc.f90:520-551
@@ -186,15 +200,19 @@ int main(int argc, char **argv)
         return 0;
     }
     for (int jt = 0; jt < npt; ++jt) {   // cdfmoc.f90:338
-        const int slot = lvvl ? 0 : jt % 3;
-        if (!lvvl && jt >= 3) drain(slot, jt - 3);
+        const int slot = lvvl ? 0 : jt % ns;
+        if (!lvvl && jt >= ns) drain(slot, jt - ns);
         if (lvvl && jt > 0) { load_e3v(jt); gpu_check(cdfmoc_gpu_set_e3v(e3v.data()), "cdfmoc_gpu_set_e3v"); }
         read_record(vf, cn.vomecrty, jt, n3, bufs[slot], raw);
         gpu_check(cdfmoc_gpu_submit(slot, jt, bufs[slot]), "cdfmoc_gpu_submit");
         if (lvvl) drain(slot, jt);   // -vvl: the area field changes per record, so only one record is in flight
     }
-    if (!lvvl) for (int jt = (npt > 3 ? npt - 3 : 0); jt < npt; ++jt) drain(jt % 3, jt);
+    if (!lvvl) for (int jt = (npt > ns ? npt - ns : 0); jt < npt; ++jt) drain(jt % ns, jt);
+    tm.mark("records");
     out.w.close();
+    for (auto p : pbuf) delete p;
     gpu_check(cdfgpu_finalize(), "cdfgpu_finalize");
+    tm.mark("close");
+    tm.total();
     return 0;
 }

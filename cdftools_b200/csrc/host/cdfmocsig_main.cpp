@@ -13,9 +13,11 @@ int main(int argc, char **argv)
     if (argc == 1) {
         printf(" usage : cdfmocsig_gpu  -v V-file -t T-file -r REF-depth | -ntr [-eiv] [-full] ...\n"
                "        ... [-sigmin sigmin] [-sigstp sigstp] [-nbins nbins] [-isodep] ...\n"
-               "        ... [-s S-file ] [-o OUT-file] [-vvl] [-verbose] [-teos10]\n");
+               "        ... [-s S-file ] [-o OUT-file] [-vvl] [-verbose] [-teos10] [-nc4]\n");
         return 0;
     }
+    PhaseTimer tm("cdfmocsig_gpu");
+    CudaWarmup warm;   // CUDA contexts come up while the mesh and mask files are read
     std::string cf_vfil, cf_tfil, cf_sfil = "none", cf_moc = "mocsig.nc", cglobal = "Partial step computation";
     float pref = 0.f, sigmin = 0.f, sigstp = 0.f;
     int nbins = 0, ii = 0;
@@ -39,6 +41,7 @@ int main(int argc, char **argv)
         else if (a == "-teos10") lteos10 = true;
         else if (a == "-isodep") lisodep = true;
         else if (a == "-verbose") lprint = true;
+        else if (a == "-nc4") note_nc4();   // DEV_TOOLS/tagnc4.tpl:1-13
         else { printf("  ERROR : %s : unknown option.\n", a.c_str()); stop(99); }
     }
     if (ii != 3) { printf("  ERROR : mandatory arguments missing, see usage please !\n"); stop(99); }
@@ -119,7 +122,10 @@ int main(int argc, char **argv)
     out.create(cf_moc, "sigma", ny, nbins, ovars, cglobal + " cdfmocsig", navlat, sigma, tim, vf);
 
     const int eos = lntr ? CDFGPU_EOS_NEUTRAL : (lteos10 ? CDFGPU_EOS_TEOS10 : CDFGPU_EOS_EOS80);
-    gpu_check(cdfgpu_init(-1, 3), "cdfgpu_init");
+    tm.mark("mesh_mask_read");
+    warm.join();
+    gpu_check(cdfgpu_init(-1, 3), "cdfgpu_init");   // $CDFGPU_DEVICES / $CDFGPU_SHARD: several devices behind the same calls
+    tm.mark("cuda_init_wait");
     gpu_check(cdfmocsig_gpu_setup(nx, ny, nz, nb, nbins, sigmin, sigstp, pref, eos, e1v.data(), lvvl ? nullptr : e3v.data(),
                                   ibmask.data(), zspv, zspt, zsps, 0, ny), "cdfmocsig_gpu_setup");
     if (lisodep) {   // gdep(:) = -getvare3(cn_fzgr, cn_gdept, npk) is formed inside the library (cdfmocsig.f90:328)
@@ -134,7 +140,9 @@ int main(int argc, char **argv)
     if (lvvl) raw = raw && vf.is_plain_f32(var_or_die(vf, "e3v"));
     gpu_check(cdfgpu_set_input_big_endian(raw ? 1 : 0), "cdfgpu_set_input_big_endian");
 
-    const int nslot = lvvl ? 1 : 3;
+    tm.mark("gpu_setup");
+    // -vvl rebuilds the resident area field per record: one record per device in flight
+    const int nslot = lvvl ? std::max(1, cdfgpu_nslots() / 3) : cdfgpu_nslots();
     std::vector<Pinned *> pv, pt, ps, pe, p3;
     for (int s = 0; s < nslot; ++s) {
         pv.push_back(new Pinned(n3)); pt.push_back(new Pinned(n3)); ps.push_back(new Pinned(n3));
@@ -169,8 +177,11 @@ int main(int argc, char **argv)
                                        lvvl ? p3[slot]->p : nullptr), "cdfmocsig_gpu_submit");
     }
     for (int jt = (npt > nslot ? npt - nslot : 0); jt < npt; ++jt) drain(jt % nslot, jt);
+    tm.mark("records");
     out.w.close();
     for (auto v : {&pv, &pt, &ps, &pe, &p3}) for (auto p : *v) delete p;
     gpu_check(cdfgpu_finalize(), "cdfgpu_finalize");
+    tm.mark("close");
+    tm.total();
     return 0;
 }

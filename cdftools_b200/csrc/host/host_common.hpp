@@ -7,7 +7,9 @@
 #include <stdlib.h>
 #include <sys/stat.h>
 
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/cdfgpu.h"
@@ -28,6 +30,44 @@ struct Names {  // modcdfnames.F90 defaults
         env("CDFT_MESH_HGR", fhgr); env("CDFT_MESH_ZGR", fzgr); env("CDFT_MASK", fmsk); env("CDFT_BASINS", fbasins);
     }
 };
+
+// $CDFGPU_TIMING=1: wall-clock seconds of the phases of a run on stderr ("<tool>: phase <name> <seconds>")
+struct PhaseTimer {
+    const char *tool;
+    bool on;
+    std::chrono::steady_clock::time_point t0, last;
+    explicit PhaseTimer(const char *t) : tool(t), on(getenv("CDFGPU_TIMING") && atoi(getenv("CDFGPU_TIMING")))
+    {
+        t0 = last = std::chrono::steady_clock::now();
+    }
+    void mark(const char *name)
+    {
+        const auto now = std::chrono::steady_clock::now();
+        if (on) fprintf(stderr, "%s: phase %s %.3f\n", tool, name, std::chrono::duration<double>(now - last).count());
+        last = now;
+    }
+    void total()
+    {
+        if (on) fprintf(stderr, "%s: phase total %.3f\n", tool, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
+
+// CUDA context creation overlaps the reading of the mesh / mask files: a helper thread creates the contexts while the
+// main thread reads; join() before cdfgpu_init
+struct CudaWarmup {
+    std::thread th;
+    CudaWarmup() : th([] { cdfgpu_warmup(); }) {}
+    void join() { if (th.joinable()) th.join(); }
+    ~CudaWarmup() { join(); }
+};
+
+// -nc4: the reference builds without key_netcdf4 accept the flag and write 64-bit-offset classic files all the same
+// (src/cdfio.F90:291-299: NF90_NETCDF4 only under the CPP key); so does this twin, and says so once
+inline void note_nc4()
+{
+    printf("  -nc4 : this build has no NetCDF-4 / HDF5 writer; output is 64-bit offset classic NetCDF, as from a\n"
+           "         reference build without key_netcdf4 (cdfio.F90:291-299)\n");
+}
 
 // chkfile (cdfio.F90:3032-3070): returns true when the file is MISSING (and says so), like the reference
 inline bool chkfile(const std::string &f, bool verbose = true)

@@ -34,6 +34,28 @@ MODULE cdfgpu
        INTEGER(C_INT), VALUE :: device, nslots
      END FUNCTION cdfgpu_init
 
+     ! one host process, several devices: shard 0 = by time record (slot s on device MOD(s, ndev)), 1 = latitude bands;
+     ! ndev = 0 reads $CDFGPU_DEVICES.  cdfgpu_init(-1, n) honours $CDFGPU_DEVICES / $CDFGPU_SHARD by itself.
+     INTEGER(C_INT) FUNCTION cdfgpu_init_multi(ndev, shard, nslots) BIND(C, NAME='cdfgpu_init_multi')
+       IMPORT :: C_INT
+       INTEGER(C_INT), VALUE :: ndev, shard, nslots
+     END FUNCTION cdfgpu_init_multi
+
+     ! creates the CUDA contexts cdfgpu_init(-1, n) will use (callable from an OpenMP task at start-up, while the mesh is read)
+     INTEGER(C_INT) FUNCTION cdfgpu_warmup() BIND(C, NAME='cdfgpu_warmup')
+       IMPORT :: C_INT
+     END FUNCTION cdfgpu_warmup
+
+     INTEGER(C_INT) FUNCTION cdfgpu_num_devices() BIND(C, NAME='cdfgpu_num_devices')
+       IMPORT :: C_INT
+     END FUNCTION cdfgpu_num_devices
+
+     ! record slots the host may keep in flight (ndev * nslots under time sharding): the DO jt loop submits record jt on
+     ! slot MOD(jt-1, cdfgpu_nslots()) and fetches in the same order
+     INTEGER(C_INT) FUNCTION cdfgpu_nslots() BIND(C, NAME='cdfgpu_nslots')
+       IMPORT :: C_INT
+     END FUNCTION cdfgpu_nslots
+
      INTEGER(C_INT) FUNCTION cdfgpu_finalize() BIND(C, NAME='cdfgpu_finalize')
        IMPORT :: C_INT
      END FUNCTION cdfgpu_finalize

@@ -23,6 +23,10 @@ EOS80, TEOS10, NEUTRAL = 0, 1, 2
 _f32p, _f64p, _i16p, _i32p = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int16), C.POINTER(C.c_int32)
 SIGNATURES = {
     "cdfgpu_init": (C.c_int, [C.c_int, C.c_int]),
+    "cdfgpu_init_multi": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "cdfgpu_warmup": (C.c_int, []),
+    "cdfgpu_num_devices": (C.c_int, []),
+    "cdfgpu_nslots": (C.c_int, []),
     "cdfgpu_finalize": (C.c_int, []),
     "cdfgpu_synchronize": (C.c_int, []),
     "cdfgpu_strerror": (C.c_char_p, [C.c_int]),
@@ -134,6 +138,19 @@ def stream_handle(stream) -> int:
 # ---- lifecycle -----------------------------------------------------------------------------------------------
 def init(device: int = -1, nslots: int = 0):
     _chk(load().cdfgpu_init(device, nslots), "cdfgpu_init")
+
+
+def init_multi(ndev: int, shard: str = "time", nslots: int = 0):
+    """One process, several devices: shard = "time" (slot s on device s mod N) or "lat" (latitude bands)."""
+    _chk(load().cdfgpu_init_multi(int(ndev), {"time": 0, "lat": 1}[shard], nslots), "cdfgpu_init_multi")
+
+
+def num_devices() -> int:
+    return int(load().cdfgpu_num_devices())
+
+
+def nslots() -> int:
+    return int(load().cdfgpu_nslots())
 
 
 def finalize():

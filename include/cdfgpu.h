@@ -20,9 +20,10 @@
  *     A buffer given to *_submit must stay untouched until the matching *_fetch returns.  Host buffers from
  *     cdfgpu_pinned_alloc() make the H2D copy asynchronous (side stream, overlaps the previous record's kernel);
  *     pageable memory works but the copy is then staged by the driver.
- *   - One process drives one GPU (cdfgpu_init(device)).  Multi-GPU runs are one process per GPU; records
- *     (time sharding) or latitude bands (band sharding: pass the band's rows, see j_first_global) are
- *     distributed by the host layer and the per-rank slabs gathered there (NCCL) -- no data-path collective.
+ *   - One process drives one GPU (cdfgpu_init(device)) or several (cdfgpu_init_multi / $CDFGPU_DEVICES: records or
+ *     latitude bands are distributed behind this ABI, results come back device -> host).  The one-process-per-GPU
+ *     deployment (torchrun) distributes records or bands in the host layer (pass the band's rows, see j_first_global)
+ *     and gathers the per-rank slabs there over NCCL.  Either way the path has no data-path collective.
  *   - Not re-entrant: call from one host thread (the reference's call sites are single-threaded).
  *   - There is NO CPU fallback: without a usable CUDA device every call fails with CDFGPU_ERR_NODEVICE.
  */
@@ -54,6 +55,19 @@ extern "C" {
 /* Select the CUDA device (device < 0: $CDFGPU_DEVICE, else 0), create the compute and copy streams.
  * nslots (1..CDFGPU_MAX_SLOTS, 0 = default 3) is the depth of the record pipeline. */
 int cdfgpu_init(int device, int nslots);
+/* ONE host process, SEVERAL devices (the reference's host is a single process looping over the records, src/cdfmoc.f90:338,
+ * src/cdfmocsig.f90:361).  cdfgpu_init(-1, n) honours $CDFGPU_DEVICES = N and $CDFGPU_SHARD = time | lat; cdfgpu_init_multi
+ * asks for it explicitly (ndev = 0: $CDFGPU_DEVICES; shard 0 = time, 1 = lat).  Devices are $CDFGPU_DEVICE .. +N-1.
+ *   time: slot s runs on device s mod N -- each device has its own record pipeline of `nslots` slots, so the host may keep
+ *         cdfgpu_nslots() = N * nslots records in flight (submit slot jt mod cdfgpu_nslots(), fetch in the same order);
+ *   lat : every record is split into N latitude bands: *_submit scatters them, *_fetch assembles the slab on the host.
+ * cdfmoc / cdfmocsig setup, set_e3v, submit, fetch, kernel_ms, -isodep work under both; cdfmoc -decomp and the cdfmaxmoc
+ * epilogue under time sharding only; the *_compute_device entry points (device pointers) need a single device.  Results are
+ * bit-identical to a single device.  The sibling tools run on the first device. */
+int cdfgpu_init_multi(int ndev, int shard, int nslots);
+int cdfgpu_warmup(void);      /* create the CUDA contexts cdfgpu_init(-1, .) will use; callable from a helper thread at start-up */
+int cdfgpu_num_devices(void); /* devices this process drives (0 before cdfgpu_init) */
+int cdfgpu_nslots(void);      /* record slots the host may keep in flight */
 int cdfgpu_finalize(void);
 int cdfgpu_synchronize(void);
 const char *cdfgpu_strerror(int code);
