@@ -172,6 +172,7 @@ struct MocPlan {
     // -decomp (cdfmoc.f90:390-517)
     bool decomp = false;
     int dec_teos10 = 0;
+    int dec_pending = -1;   // slot whose decomposition has been submitted and not fetched yet
     float *d_e1u = nullptr, *d_zcoef = nullptr, *d_zt = nullptr, *d_zs = nullptr, *d_sig = nullptr, *d_hdep = nullptr,
           *d_zvgeo = nullptr;
     int16_t *d_umask = nullptr, *d_tmask = nullptr;
@@ -784,6 +785,10 @@ static int cdfmoc_gpu_decomp_submit_dev(int slot, int jt, const float *zv, const
     REQUIRE_INIT();
     REQUIRE(moc.ready && moc.decomp, CDFGPU_ERR_STATE, "cdfmoc_gpu_decomp_submit: cdfmoc_gpu_decomp_setup has not been called");
     REQUIRE(zt && zs, CDFGPU_ERR_ARG, "cdfmoc_gpu_decomp_submit: null pointer");
+    // The component slabs (sh, bt, ag) and the working fields of the decomposition are plan-wide, not per slot: one
+    // decomposition is in flight per device at a time -- a second submit before the fetch would overwrite the first's results
+    REQUIRE(moc.dec_pending < 0 || moc.dec_pending == slot, CDFGPU_ERR_STATE,
+            "cdfmoc_gpu_decomp_submit: another slot's decomposition has not been fetched yet (one record in flight per device)");
     int rc = cdfmoc_gpu_submit_dev(slot, jt, zv);   // total MOC (cdfmoc.f90:352-388) into the slot's slab
     if (rc) return rc;
     rc = ensure_eos(moc.dec_teos10, g.s_compute);
@@ -824,6 +829,7 @@ static int cdfmoc_gpu_decomp_submit_dev(int slot, int jt, const float *zv, const
     CDF_CUDA(cudaGetLastError());
     g.launches += 5;
     CDF_CUDA(cudaEventRecord(s.ev_k1, st));
+    moc.dec_pending = slot;
     return CDFGPU_OK;
 }
 
@@ -832,6 +838,8 @@ static int cdfmoc_gpu_decomp_fetch_dev(int slot, double *dmoc, double *dmoc_sh, 
     REQUIRE_INIT();
     REQUIRE(moc.ready && moc.decomp, CDFGPU_ERR_STATE, "cdfmoc_gpu_decomp_fetch: cdfmoc_gpu_decomp_setup has not been called");
     REQUIRE(dmoc && dmoc_sh && dmoc_bt && dmoc_ag, CDFGPU_ERR_ARG, "cdfmoc_gpu_decomp_fetch: null pointer");
+    REQUIRE(moc.dec_pending == slot, CDFGPU_ERR_STATE,
+            "cdfmoc_gpu_decomp_fetch: this slot holds no pending decomposition (the components belong to the latest decomp_submit)");
     int rc = cdfmoc_gpu_fetch_dev(slot, dmoc);
     if (rc) return rc;
     const size_t nb8 = moc.out_elems() * sizeof(double);
@@ -839,6 +847,7 @@ static int cdfmoc_gpu_decomp_fetch_dev(int slot, double *dmoc, double *dmoc_sh, 
     CDF_CUDA(cudaMemcpyAsync(dmoc_bt, moc.d_bt, nb8, cudaMemcpyDeviceToHost, g.s_d2h));
     CDF_CUDA(cudaMemcpyAsync(dmoc_ag, moc.d_ag, nb8, cudaMemcpyDeviceToHost, g.s_d2h));
     CDF_CUDA(cudaStreamSynchronize(g.s_d2h));
+    moc.dec_pending = -1;
     return CDFGPU_OK;
 }
 

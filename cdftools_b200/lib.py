@@ -240,8 +240,9 @@ def cdfmoc_kernel_ms(slot: int) -> float:
 def cdfmoc_decomp_setup(e1u, gphiv, gdept, umask, tmask, teos10=False):
     """umask, tmask: int16 (>= nz-1, ny, nx) planes as the reference reads them (cdfmoc.f90:439-440)."""
     assert umask.dtype == np.int16 and tmask.dtype == np.int16 and e1u.dtype == np.float32
-    _chk(load().cdfmoc_gpu_decomp_setup(int(teos10), _ptr(e1u), _ptr(np.ascontiguousarray(gphiv, np.float32)),
-                                        _ptr(np.ascontiguousarray(gdept, np.float32)), _ptr(umask), _ptr(tmask)),
+    gphiv32 = np.ascontiguousarray(gphiv, np.float32)   # held in locals: a converted temporary must outlive the C call
+    gdept32 = np.ascontiguousarray(gdept, np.float32)
+    _chk(load().cdfmoc_gpu_decomp_setup(int(teos10), _ptr(e1u), _ptr(gphiv32), _ptr(gdept32), _ptr(umask), _ptr(tmask)),
          "cdfmoc_gpu_decomp_setup")
 
 
@@ -308,8 +309,8 @@ def cdfmocsig_fetch(slot, out):
 
 
 def cdfmocsig_set_isodep(gdept):
-    _chk(load().cdfmocsig_gpu_set_isodep(_ptr(None if gdept is None else np.ascontiguousarray(gdept, np.float32))),
-         "cdfmocsig_gpu_set_isodep")
+    gdept32 = None if gdept is None else np.ascontiguousarray(gdept, np.float32)   # kept alive across the C call
+    _chk(load().cdfmocsig_gpu_set_isodep(_ptr(gdept32)), "cdfmocsig_gpu_set_isodep")
 
 
 def cdfmocsig_fetch_isodep(slot, out):

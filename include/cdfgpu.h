@@ -108,7 +108,8 @@ int cdfgpu_microbench(int kind, double *out3);
  * fetch   blocks until the slot's record is done and writes dmoc(nb,ny,nz) in Sv, already integrated from the
  *         bottom (cdfmoc.f90:382-388); dmoc(:,:,nz) = 0.
  * compute_device: same kernel on a record that is already in device memory (d_zv, d_dmoc device pointers,
- *         `stream` a cudaStream_t or NULL for the library's compute stream); asynchronous.
+ *         `stream` a cudaStream_t or NULL for the library's compute stream); asynchronous.  All compute_device calls on
+ *         caller streams share one set of scheduling counters: issue them on ONE stream (or order the streams yourself).
  * Consecutive cdfmoc (and cdfmocsig) kernels of one stream are launched with programmatic stream serialization: the
  * next one may start while the previous one drains, but stores nothing before its predecessor is complete, so stream
  * order holds for every consumer (copies, events, kernels launched the ordinary way), and two launches may share an
@@ -131,6 +132,8 @@ int cdfmoc_gpu_maxmoc(int slot, int basin, int ijmin, int ijmax, int ikmin, int 
  * decomp_setup (after cdfmoc_gpu_setup): e1u, gphiv (nx,ny); gdept (nz); umask, tmask (nx,ny,nz-1 levels used) as the
  *   INTEGER(2) planes the reference reads level by level (:439-440); teos10 selects the EOS of sigmai (:443).
  * decomp_submit: one record of V, T, S (nx,ny,nz-1); computes the total MOC and the three components.
+ *   ONE decomposition is in flight per device: the component slabs are plan-wide, so a decomp_submit on another slot
+ *   before the pending one is fetched (and a decomp_fetch of any other slot) fails with CDFGPU_ERR_STATE.
  * decomp_fetch : dmoc, dmoc_sh, dmoc_bt, dmoc_ag, each (nb,ny,nz) in Sv.  dmoc_sh starts from zero for every record
  *   (the reference never initialises it, cdfmoc.f90:299,471, which is only meaningful for a single record). */
 int cdfmoc_gpu_decomp_setup(int teos10, const float *e1u, const float *gphiv, const float *gdept, const int16_t *umask,

@@ -178,6 +178,18 @@ def test_cdfmoc_decomp(gpu_lib, oracle_mod, grid, teos10):
         got = gpu_lib.cdfmoc_decomp_fetch(0, (nz, ny, nb))
         for k in ("total", "bt", "sh", "ag"):
             assert_psi_close(got[k], ref[k], f"{grid} decomp {k} rec {rec}")
+    # one decomposition in flight per device: the component slabs are plan-wide, so a second slot is refused until the
+    # first has been fetched, and a fetch of a slot without a pending decomposition is refused too
+    gpu_lib.cdfmoc_decomp_submit(0, 2, v, t, s)
+    with pytest.raises(gpu_lib.CdfGpuError) as e:
+        gpu_lib.cdfmoc_decomp_submit(1, 3, v, t, s)
+    assert e.value.code == 3
+    with pytest.raises(gpu_lib.CdfGpuError):
+        gpu_lib.cdfmoc_decomp_fetch(1, (nz, ny, nb))
+    got = gpu_lib.cdfmoc_decomp_fetch(0, (nz, ny, nb))
+    assert_psi_close(got["sh"], ref["sh"], "pending slot fetched after the refused submit")
+    gpu_lib.cdfmoc_decomp_submit(1, 3, v, t, s)
+    assert_psi_close(gpu_lib.cdfmoc_decomp_fetch(1, (nz, ny, nb))["ag"], ref["ag"], "second slot after the fetch")
     # the plain path still works on the same plan afterwards
     out = np.empty((nz, ny, nb))
     gpu_lib.cdfmoc_submit(1, 2, v)
