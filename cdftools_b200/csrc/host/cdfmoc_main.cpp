@@ -88,7 +88,7 @@ int main(int argc, char **argv)
     std::vector<float> e3v(nxy * nz), lev(nxy);
     auto load_e3v = [&](long rec) {
         nc3::Reader *src = lvvl ? &vf : &zgr.nc;
-        const std::string name = lvvl ? "e3v" : zgr.e3v_name();
+        const std::string name = lvvl ? cn.ve3vvvl : zgr.e3v_name();
         for (int k = 0; k < nz; ++k) {
             float *dst = e3v.data() + (size_t)k * nxy;
             if (lfull) for (size_t c = 0; c < nxy; ++c) dst[c] = e31d[k];
@@ -130,13 +130,13 @@ int main(int argc, char **argv)
     gpu_check(cdfgpu_set_input_big_endian(raw ? 1 : 0), "cdfgpu_set_input_big_endian");
     if (ldec) {   // extra fields of the decomposition (cdfmoc.f90:312-313,439-442)
         std::vector<float> e1u(nxy), gdept(nz);
-        read_level(hgr, "e1u", 0, 0, nxy, e1u.data());
+        read_level(hgr, cn.e1u, 0, 0, nxy, e1u.data());
         read_1d(zgr.nc, zgr.name1d("gdept"), nz, gdept.data());
         std::vector<int16_t> um(n3), tm(n3);
         for (int k = 0; k < nz - 1; ++k) {
-            read_level(msk, "umask", k, 0, nxy, lev.data());
+            read_level(msk, cn.umask, k, 0, nxy, lev.data());
             for (size_t c = 0; c < nxy; ++c) um[(size_t)k * nxy + c] = (int16_t)lev[c];
-            read_level(msk, "tmask", k, 0, nxy, lev.data());
+            read_level(msk, cn.tmask, k, 0, nxy, lev.data());
             for (size_t c = 0; c < nxy; ++c) tm[(size_t)k * nxy + c] = (int16_t)lev[c];
         }
         gpu_check(cdfmoc_gpu_decomp_setup(lteos10 ? 1 : 0, e1u.data(), gphiv.data(), gdept.data(), um.data(), tm.data()),

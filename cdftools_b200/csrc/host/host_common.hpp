@@ -7,7 +7,12 @@
 #include <stdlib.h>
 #include <sys/stat.h>
 
+#include <ctype.h>
+
 #include <chrono>
+#include <fstream>
+#include <map>
+#include <sstream>
 #include <string>
 #include <thread>
 #include <vector>
@@ -20,14 +25,113 @@ namespace cdfhost {
 struct Names {  // modcdfnames.F90 defaults
     std::string x = "x", y = "y", z = "depth", t = "time_counter";
     std::string vomecrty = "vomecrty", vomeeivv = "vomeeivv", votemper = "votemper", vosaline = "vosaline";
-    std::string e1v = "e1v", gphiv = "gphiv", vmask = "vmask", tmaskatl = "tmaskatl", tmaskind = "tmaskind",
-                tmaskpac = "tmaskpac", vtimec = "time_counter", vdepthw = "depthw", vlon2d = "nav_lon", vlat2d = "nav_lat";
+    std::string e1v = "e1v", e1u = "e1u", gphiv = "gphiv", vmask = "vmask", umask = "umask", tmask = "tmask", tmaskatl = "tmaskatl",
+                tmaskind = "tmaskind", tmaskpac = "tmaskpac", vtimec = "time_counter", vdepthw = "depthw", vlon2d = "nav_lon",
+                vlat2d = "nav_lat", ve3v = "e3v", ve3vvvl = "e3v", ve3t1d = "e3t", gdept = "gdept", gdepw = "gdepw";
     std::string fhgr = "mesh_hgr.nc", fzgr = "mesh_zgr.nc", fmsk = "mask.nc", fbasins = "new_maskglo.nc";
     std::string missing = "_FillValue";
     Names()
-    {  // chkenv, modcdfnames.F90:376-380
+    {
+        read_cdf_names();
+        chkenv();
+    }
+    void chkenv()
+    {  // modcdfnames.F90:376-380
         auto env = [](const char *n, std::string &dst) { const char *e = getenv(n); if (e && *e) dst = e; };
         env("CDFT_MESH_HGR", fhgr); env("CDFT_MESH_ZGR", fzgr); env("CDFT_MASK", fmsk); env("CDFT_BASINS", fbasins);
+    }
+    // ReadCdfNames (modcdfnames.F90:268-326): the namelist nam_cdf_names ($NAM_CDF_NAMES) in the current directory, else in
+    // $HOME/CDFTOOLS_cfg/, renames dimensions, variables and mesh / mask files.  The reference READs the groups namdim,
+    // namdimvar, nammetrics, namvars, nambathy, namsqdvar and nammeshmask (NOT nammask: the mask variable names cannot be
+    // changed this way there either); unknown keys are ignored here where the Fortran run-time would stop.
+    void read_cdf_names()
+    {
+        std::string nam = "nam_cdf_names";
+        if (const char *e = getenv("NAM_CDF_NAMES")) if (*e) nam = e;
+        struct stat st;
+        if (stat(nam.c_str(), &st) != 0) {
+            const char *home = getenv("HOME");
+            nam = std::string(home ? home : "") + "/CDFTOOLS_cfg/" + nam;
+            if (stat(nam.c_str(), &st) != 0) return;
+        }
+        printf("  CAUTION : dim names and variable names are now set according to \n  =======   the following namelist : %s\n", nam.c_str());
+        std::ifstream f(nam);
+        std::stringstream ss;
+        ss << f.rdbuf();
+        const std::map<std::string, std::map<std::string, std::string *>> groups = {
+            {"namdim", {{"cn_x", &x}, {"cn_y", &y}, {"cn_z", &z}, {"cn_t", &t}}},
+            {"namdimvar", {{"cn_vlon2d", &vlon2d}, {"cn_vlat2d", &vlat2d}, {"cn_vdepthw", &vdepthw}, {"cn_vtimec", &vtimec},
+                           {"cn_missing_value", &missing}}},
+            {"nammetrics", {{"cn_ve1v", &e1v}, {"cn_ve1u", &e1u}, {"cn_gphiv", &gphiv}, {"cn_ve3v", &ve3v}, {"cn_ve3vvvl", &ve3vvvl},
+                            {"cn_ve3t1d", &ve3t1d}, {"cn_gdept", &gdept}, {"cn_gdepw", &gdepw}}},
+            {"namvars", {{"cn_vomecrty", &vomecrty}, {"cn_vomeeivv", &vomeeivv}, {"cn_votemper", &votemper}, {"cn_vosaline", &vosaline}}},
+            {"nammeshmask", {{"cn_fzgr", &fzgr}, {"cn_fhgr", &fhgr}, {"cn_fmsk", &fmsk}, {"cn_fbasins", &fbasins}}},
+        };
+        parse_namelist(ss.str(), groups);
+    }
+    // a Fortran namelist file, as far as character assignments go:  &group  key = 'value' [,] ...  /   ; ! starts a comment
+    static void parse_namelist(const std::string &txt, const std::map<std::string, std::map<std::string, std::string *>> &groups)
+    {
+        auto lower = [](std::string v) { for (auto &c : v) c = (char)tolower((unsigned char)c); return v; };
+        std::string clean;   // comments out (outside quotes)
+        {
+            char q = 0;
+            bool com = false;
+            for (char c : txt) {
+                if (com) { if (c == '\n') { com = false; clean += c; } continue; }
+                if (q) { if (c == q) q = 0; clean += c; continue; }
+                if (c == '\'' || c == '"') { q = c; clean += c; continue; }
+                if (c == '!') { com = true; continue; }
+                clean += c;
+            }
+        }
+        size_t pos = 0;
+        while ((pos = clean.find('&', pos)) != std::string::npos) {
+            size_t e = pos + 1;
+            while (e < clean.size() && (isalnum((unsigned char)clean[e]) || clean[e] == '_')) ++e;
+            const std::string gname = lower(clean.substr(pos + 1, e - pos - 1));
+            // the group ends at the first '/' outside quotes (or at "&end")
+            size_t end = e;
+            char q = 0;
+            for (; end < clean.size(); ++end) {
+                const char c = clean[end];
+                if (q) { if (c == q) q = 0; continue; }
+                if (c == '\'' || c == '"') { q = c; continue; }
+                if (c == '/' || c == '&') break;
+            }
+            const std::string body = clean.substr(e, end - e);
+            pos = end + 1;
+            const auto git = groups.find(gname);
+            if (git == groups.end()) continue;
+            size_t p2 = 0;
+            while (p2 < body.size()) {
+                const size_t eq = body.find('=', p2);
+                if (eq == std::string::npos) break;
+                size_t k1 = eq;
+                while (k1 > p2 && isspace((unsigned char)body[k1 - 1])) --k1;
+                size_t k0 = k1;
+                while (k0 > p2 && (isalnum((unsigned char)body[k0 - 1]) || body[k0 - 1] == '_')) --k0;
+                const std::string key = lower(body.substr(k0, k1 - k0));
+                size_t v0 = eq + 1;
+                while (v0 < body.size() && isspace((unsigned char)body[v0])) ++v0;
+                std::string val;
+                size_t v1 = v0;
+                if (v0 < body.size() && (body[v0] == '\'' || body[v0] == '"')) {
+                    const char qq = body[v0];
+                    v1 = body.find(qq, v0 + 1);
+                    if (v1 == std::string::npos) break;
+                    val = body.substr(v0 + 1, v1 - v0 - 1);
+                    ++v1;
+                } else {
+                    while (v1 < body.size() && !isspace((unsigned char)body[v1]) && body[v1] != ',') ++v1;
+                    val = body.substr(v0, v1 - v0);
+                }
+                while (!val.empty() && val.back() == ' ') val.pop_back();   // CHARACTER(LEN=256) values are used TRIMmed
+                const auto kit = git->second.find(key);
+                if (kit != git->second.end()) *kit->second = val;
+                p2 = v1;
+            }
+        }
     }
 };
 
@@ -95,23 +199,30 @@ inline void nc_check(bool ok, const std::string &err)
 
 struct MeshZgr {
     nc3::Reader nc;
-    std::string ver;  // v3.0 | v3.6 (v2.0 partial-step files are not supported by this twin)
+    std::string ver;   // v2.0 | v3.0 | v3.6  (SetMeshZgrVersion, cdfio.F90:3310-3335)
     void open(const std::string &path)
     {
         nc_check(nc.open(path), nc.err);
         const int iv = nc.find_var("e3t_0");
-        if (iv < 0) { printf(" ERROR : %s is a v2.0 mesh_zgr file (e3v_ps): not supported by the GPU twin\n", path.c_str()); stop(98); }
-        int nsp = 0;  // number of non-record, non-singleton dims
-        for (int d : nc.vars[iv].dimids) if (nc.dims[d].len > 1 && d != nc.recdim) ++nsp;
-        ver = (nsp <= 1) ? "v3.0" : "v3.6";
+        if (iv < 0) ver = "v2.0";   // IOIPSL-style file: e3._ps, gdept / gdepw / e3t as (t,z,1,1) columns
+        else {
+            int nsp = 0;  // number of non-record, non-singleton dims
+            for (int d : nc.vars[iv].dimids) if (nc.dims[d].len > 1 && d != nc.recdim) ++nsp;
+            ver = (nsp <= 1) ? "v3.0" : "v3.6";
+        }
         printf("  mesh_zgr version is %s\n", ver.c_str());
     }
-    std::string e3v_name() const { return ver == "v3.0" ? "e3v" : "e3v_0"; }
-    std::string name1d(const std::string &base) const  // gdepw / gdept / e3t1d
+    // getvar(..., ldiom=.true.) maps cn_ve3v (cdfio.F90:1522-1527)
+    std::string e3v_name(const std::string &cn_ve3v = "e3v") const
     {
-        if (base == "gdepw") return ver == "v3.0" ? "gdepw_0" : "gdepw_1d";
-        if (base == "gdept") return ver == "v3.0" ? "gdept_0" : "gdept_1d";
-        return ver == "v3.0" ? "e3t_0" : "e3t_1d";
+        (void)cn_ve3v;
+        return ver == "v2.0" ? "e3v_ps" : ver == "v3.0" ? "e3v" : "e3v_0";
+    }
+    std::string name1d(const std::string &base) const  // getvare3 (cdfio.F90:2232-2274): gdepw / gdept / e3t1d
+    {
+        if (base == "gdepw") return ver == "v2.0" ? "gdepw" : ver == "v3.0" ? "gdepw_0" : "gdepw_1d";
+        if (base == "gdept") return ver == "v2.0" ? "gdept" : ver == "v3.0" ? "gdept_0" : "gdept_1d";
+        return ver == "v2.0" ? "e3t" : ver == "v3.0" ? "e3t_0" : "e3t_1d";
     }
 };
 

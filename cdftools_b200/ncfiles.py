@@ -19,7 +19,9 @@ def _new(path, dims, version=2):
     return f
 
 
-def write_mesh(m: synth.Mesh, outdir, with_basins=True, version=2):
+def write_mesh(m: synth.Mesh, outdir, with_basins=True, version=2, zgr="v3.6"):
+    """zgr: the mesh_zgr flavour SetMeshZgrVersion tells apart (src/cdfio.F90:3310-3335): "v3.6" (e3v_0, *_1d), "v3.0"
+    (e3v, gdepw_0 / gdept_0 / e3t_0 as (t,z) columns) or "v2.0" (e3v_ps, gdepw / gdept / e3t as (t,z,1,1))."""
     out = Path(outdir)
     out.mkdir(parents=True, exist_ok=True)
     nz, ny, nx = m.e3v_0.shape
@@ -30,12 +32,24 @@ def write_mesh(m: synth.Mesh, outdir, with_basins=True, version=2):
         v = f.createVariable(name, "f", ("t", "y", "x"))
         v[0] = arr
     f.close()
-    f = _new(out / "mesh_zgr.nc", {"x": nx, "y": ny, "z": nz, "t": None}, version)
-    v = f.createVariable("e3v_0", "f", ("t", "z", "y", "x")); v[0] = m.e3v_0
-    v = f.createVariable("e3u_0", "f", ("t", "z", "y", "x")); v[0] = (m.e3v_0 * np.float32(1.01)).astype(np.float32)
-    v = f.createVariable("e3t_0", "f", ("t", "z", "y", "x")); v[0] = m.e3v_0     # presence + rank select 'v3.6'
-    for name, arr in (("gdepw_1d", m.gdepw_1d), ("gdept_1d", m.gdept_1d), ("e3t_1d", m.e3t_1d)):
-        v = f.createVariable(name, "f", ("t", "z")); v[0] = arr
+    f = _new(out / "mesh_zgr.nc", {"x": nx, "y": ny, "z": nz, "t": None, **({"x_a": 1, "y_a": 1} if zgr == "v2.0" else {})}, version)
+    e3u = (m.e3v_0 * np.float32(1.01)).astype(np.float32)
+    if zgr == "v3.6":
+        v = f.createVariable("e3v_0", "f", ("t", "z", "y", "x")); v[0] = m.e3v_0
+        v = f.createVariable("e3u_0", "f", ("t", "z", "y", "x")); v[0] = e3u
+        v = f.createVariable("e3t_0", "f", ("t", "z", "y", "x")); v[0] = m.e3v_0     # presence + rank select 'v3.6'
+        for name, arr in (("gdepw_1d", m.gdepw_1d), ("gdept_1d", m.gdept_1d), ("e3t_1d", m.e3t_1d)):
+            v = f.createVariable(name, "f", ("t", "z")); v[0] = arr
+    elif zgr == "v3.0":
+        v = f.createVariable("e3v", "f", ("t", "z", "y", "x")); v[0] = m.e3v_0
+        v = f.createVariable("e3u", "f", ("t", "z", "y", "x")); v[0] = e3u
+        for name, arr in (("gdepw_0", m.gdepw_1d), ("gdept_0", m.gdept_1d), ("e3t_0", m.e3t_1d)):   # e3t_0 of rank 1: 'v3.0'
+            v = f.createVariable(name, "f", ("t", "z")); v[0] = arr
+    else:
+        v = f.createVariable("e3v_ps", "f", ("t", "z", "y", "x")); v[0] = m.e3v_0
+        v = f.createVariable("e3u_ps", "f", ("t", "z", "y", "x")); v[0] = e3u
+        for name, arr in (("gdepw", m.gdepw_1d), ("gdept", m.gdept_1d), ("e3t", m.e3t_1d)):        # no e3t_0 at all: 'v2.0'
+            v = f.createVariable(name, "f", ("t", "z", "y_a", "x_a")); v[0, :, 0, 0] = arr
     f.close()
     f = _new(out / "mask.nc", {"x": nx, "y": ny, "z": nz, "t": None}, version)
     for name, arr in (("vmask", m.vmask), ("tmask", m.tmask), ("umask", m.umask)):
@@ -48,7 +62,7 @@ def write_mesh(m: synth.Mesh, outdir, with_basins=True, version=2):
         f.close()
 
 
-def write_gridv(m: synth.Mesh, path, nrec, spval=0.0, adversarial=False, eiv=False, version=2, first=0):
+def write_gridv(m: synth.Mesh, path, nrec, spval=0.0, adversarial=False, eiv=False, version=2, first=0, vname="vomecrty"):
     nz, ny, nx = m.e3v_0.shape
     f = _new(path, {"x": nx, "y": ny, "depthv": nz, "time_counter": None}, version)
     f.start_date = np.int32(20260101)
@@ -57,7 +71,7 @@ def write_gridv(m: synth.Mesh, path, nrec, spval=0.0, adversarial=False, eiv=Fal
     f.CASE = "B200"
     tc = f.createVariable("time_counter", "d", ("time_counter",))
     tc.units = "seconds since 2026-01-01 00:00:00"
-    v = f.createVariable("vomecrty", "f", ("time_counter", "depthv", "y", "x"))
+    v = f.createVariable(vname, "f", ("time_counter", "depthv", "y", "x"))
     v.missing_value = np.float32(spval)
     e = None
     if eiv:

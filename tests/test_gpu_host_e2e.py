@@ -312,3 +312,54 @@ def test_cdftransig_cli_matches_oracle(tools, oracle_mod, tmp_path, args, code):
         assert np.array_equal(got != 0, want != 0), name
         assert np.allclose(got, want, rtol=2e-7, atol=1e-6), (name, np.abs(got - want).max())
     f.close()
+
+
+@pytest.mark.parametrize("zgr", ["v3.0", "v2.0"])
+def test_cdfmoc_cli_older_mesh_zgr_flavours(tools, oracle_mod, tmp_path, zgr):
+    """SetMeshZgrVersion (src/cdfio.F90:3310-3335) and the name mapping of getvar / getvare3 (:1510-1536, :2226-2274):
+    v3.0 (e3v, gdepw_0 ...) and v2.0 (e3v_ps, gdepw ... as (t,z,1,1) columns) mesh_zgr files give the v3.6 result."""
+    m = synth.make_mesh("SMALL")
+    ncfiles.write_mesh(m, tmp_path, zgr=zgr)
+    recs = ncfiles.write_gridv(m, tmp_path / "gridV.nc", 2)
+    out = _run(tools["cdfmoc_gpu"], ["-v", "gridV.nc"], tmp_path)
+    assert "mesh_zgr version is " + zgr in out
+    ib, e3m = case_inputs(oracle_mod, m, synth)
+    f = netcdf_file(str(tmp_path / "moc.nc"), "r", mmap=False)
+    ref = oracle_mod.cdfmoc_output(oracle_mod.cdfmoc_record(m.e1v, e3m, ib, recs[1][:-1]))
+    assert np.allclose(f.variables["zomsfglo"][1, :, :, 0], ref[0], rtol=2e-7, atol=1e-6)
+    assert np.allclose(f.variables["depthw"][:], -m.gdepw_1d)
+    f.close()
+    # the full-step option reads the 1-D e3t through the same mapping
+    _run(tools["cdfmoc_gpu"], ["-v", "gridV.nc", "-full", "-o", "full.nc"], tmp_path)
+    e3full = np.broadcast_to(m.e3t_1d[:, None, None], m.e3v_0.shape).astype(np.float32)
+    f = netcdf_file(str(tmp_path / "full.nc"), "r", mmap=False)
+    ref = oracle_mod.cdfmoc_output(oracle_mod.cdfmoc_record(m.e1v, oracle_mod.mask_e3v(e3full, m.vmask.astype(np.float32)), ib, recs[0][:-1]))
+    assert np.allclose(f.variables["zomsfatl"][0, :, :, 0], ref[1], rtol=2e-7, atol=1e-6)
+    f.close()
+
+
+def test_cdfmoc_cli_nam_cdf_names_and_nc4(tools, oracle_mod, tmp_path):
+    """ReadCdfNames (src/modcdfnames.F90:268-326): a nam_cdf_names namelist in the working directory renames variables and
+    mesh files; CDFT_* environment variables still win (chkenv runs after it); -nc4 is accepted (DEV_TOOLS/tagnc4.tpl)."""
+    m = synth.make_mesh("SMALL")
+    ncfiles.write_mesh(m, tmp_path)
+    (tmp_path / "mesh_hgr.nc").rename(tmp_path / "my_hgr.nc")
+    (tmp_path / "mask.nc").rename(tmp_path / "env_mask.nc")
+    recs = ncfiles.write_gridv(m, tmp_path / "gridV.nc", 2, vname="vo")
+    (tmp_path / "nam_cdf_names").write_text(
+        "! names of this configuration\n&namdim\n/\n&namdimvar\n cn_vdepthw = 'depthw'  ! unchanged\n/\n&nammetrics\n/\n"
+        "&NAMVARS\n  cn_vomecrty='vo' , cn_votemper = \"thetao\"\n/\n&nambathy\n/\n&namsqdvar\n/\n"
+        "&nammeshmask\n cn_fhgr = 'my_hgr.nc'\n cn_fmsk = 'not_there.nc'\n/\n")
+    r = subprocess.run([tools["cdfmoc_gpu"], "-v", "gridV.nc", "-nc4"], capture_output=True, text=True, cwd=tmp_path,
+                       env=dict(os.environ, CDFT_MASK="env_mask.nc"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "nam_cdf_names" in r.stdout and "-nc4" in r.stdout
+    ib, e3m = case_inputs(oracle_mod, m, synth)
+    f = netcdf_file(str(tmp_path / "moc.nc"), "r", mmap=False)
+    ref = oracle_mod.cdfmoc_output(oracle_mod.cdfmoc_record(m.e1v, e3m, ib, recs[0][:-1]))
+    assert np.allclose(f.variables["zomsfglo"][0, :, :, 0], ref[0], rtol=2e-7, atol=1e-6)
+    f.close()
+    # without the namelist the renamed variable is not found: STOP 98 like the reference
+    (tmp_path / "nam_cdf_names").unlink()
+    r = subprocess.run([tools["cdfmoc_gpu"], "-v", "gridV.nc"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 99 and "mesh_hgr.nc is missing" in r.stdout
