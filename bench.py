@@ -235,7 +235,8 @@ class Ctx:
         if self.world > 1:
             # the slab gather is small next to the kernels' traffic: a few NCCL channels keep it off the SMs the persistent
             # kernels occupy (each channel is a resident CTA)
-            os.environ.setdefault("NCCL_MAX_NCHANNELS", str(args.nccl_channels))
+            if args.nccl_channels > 0:
+                os.environ.setdefault("NCCL_MAX_NCHANNELS", str(args.nccl_channels))
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
         lib.init(self.local, 3)
         lib.set_device_inputs_ready(True)   # records are resident and synchronised before the timed launches
@@ -326,14 +327,23 @@ def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=T
     # ---- the slab gather to rank 0 (the only communication of the path): records go in a few groups, each group's
     # slabs right behind its kernels on a side stream, into receive buffers allocated ONCE -- only the last group of the
     # last step is not overlapped by kernels
-    ngroups = 1 if world == 1 else max(1, min(4, nrec // 2))
+    ngroups = 1 if world == 1 else max(1, min(args.gather_groups, nrec // 2))
+    do_gather = world > 1 and not args.no_gather
     gb = [(g * nrec) // ngroups for g in range(ngroups + 1)]
     recv, full = None, None
-    if world > 1 and rank == 0:
-        gmax = max(gb[g + 1] - gb[g] for g in range(ngroups))
-        recv = [torch.empty((gmax,) + out_shape, dtype=torch.float64, device="cuda") for _ in range(world)]
+    # What travels is what the writer needs: the output files hold REAL(4) (src/cdfmoc.f90:520-551 REAL(dmoc(...)) and the
+    # derived inp0 = REAL(glo - atl); src/cdfmocsig.f90:478-483), so the slabs are converted on the device (fp64 difference
+    # first, then the rounding, as the reference does) and half the bytes cross NVLink.  --gather-dtype f64 sends them raw.
+    g32 = args.gather_dtype == "f32"
+    nvar = (nb + 1 if (not sig and nb >= 5) else nb) if g32 else nb
+    gshape = out_shape[:-1] + (nvar,)
+    gdtype = torch.float32 if g32 else torch.float64
+    gmax = max(gb[g + 1] - gb[g] for g in range(ngroups))
+    send = torch.empty((gmax,) + gshape, dtype=gdtype, device="cuda") if (do_gather and g32) else None
+    if do_gather and rank == 0:
+        recv = [torch.empty((gmax,) + gshape, dtype=gdtype, device="cuda") for _ in range(world)]
         if band:
-            full = torch.empty((nrec, nyg) + out_shape[1:], dtype=torch.float64, device="cuda")
+            full = torch.empty((nrec, nyg) + gshape[1:], dtype=gdtype, device="cuda")
     gather_events = []
 
     def launch(rec, o):
@@ -342,22 +352,37 @@ def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=T
         else:
             lib.cdfmoc_compute_device(rec[0], o, st)
 
+    diff64 = torch.empty((gmax,) + out_shape[:-1], dtype=torch.float64, device="cuda") if (do_gather and g32 and nvar > nb) else None
+    gathered = [None, None]   # per output buffer: the event that marks its last gather as complete
+
     def kernel_step(i):
         o = outs[i & 1]
+        if gathered[i & 1] is not None:
+            st.wait_event(gathered[i & 1])   # this buffer's slabs of two steps ago must have left before it is overwritten
         for g in range(ngroups):
             with torch.cuda.stream(st):
                 for r in range(gb[g], gb[g + 1]):
                     launch(recs[r % n_res], o[r])
-            if world > 1:
+            if do_gather:
                 ev = torch.cuda.Event()
                 ev.record(st)
                 with torch.cuda.stream(comm):
                     comm.wait_event(ev)
                     part = o[gb[g]:gb[g + 1]]
+                    if g32:   # output conversion on the device: REAL(psi), and inp0 = REAL(psi_glo - psi_atl) for cdfmoc
+                        p32 = send[: part.shape[0]]
+                        p32[..., :nb].copy_(part)
+                        if nvar > nb:
+                            torch.sub(part[..., 0], part[..., 1], out=diff64[: part.shape[0]])
+                            p32[..., nb].copy_(diff64[: part.shape[0]])
+                        part = p32
                     dist.gather(part, [b[: part.shape[0]] for b in recv] if rank == 0 else None, dst=0)
                     if band and rank == 0:   # unpack the padded bands into the (record, j, bin, basin) array the writer wants
                         for rr, (b0, b1) in enumerate(bands):
                             full[gb[g]:gb[g + 1], b0:b1].copy_(recv[rr][: part.shape[0], : b1 - b0])
+        if do_gather:
+            gathered[i & 1] = torch.cuda.Event()
+            gathered[i & 1].record(comm)
 
     def sync_all():
         st.synchronize()
@@ -484,7 +509,7 @@ def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=T
         parity = {"rows_checked": int(len(cand)), "max_abs_err_sv": max(errs), "within_tolerance": ok,
                   "tolerance": "1e-9 relative or 1e-6 Sv"}
         if band and full is not None:   # the gathered array on rank 0 holds every band: rank 0's own rows must be in place
-            parity["gathered_equals_local"] = bool(torch.equal(full[0, j0:j1], outs[(steps - 1) & 1][0, : j1 - j0]))
+            parity["gathered_equals_local"] = bool(torch.equal(full[0, j0:j1, :, :nb], outs[(steps - 1) & 1][0, : j1 - j0].to(gdtype)))
 
     # ---- cdfmocsig only: the same kernel on T/S as smooth as the stratification (no cell-to-cell noise), one untimed
     # and one timed pass over the resident records.  The headline `value` stays the white-noise case (worst case for the
@@ -543,8 +568,10 @@ def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=T
                             % (n_res * rec_bytes / 1e9),
                       "sharding": ("latitude bands + NCCL slab gather" if band else
                                    "time (each rank owns its own records) + NCCL slab gather") if world > 1 else "single GPU",
-                      "gather": ("%d group(s) per step behind their kernels, preallocated receive buffers, "
-                                 "NCCL_MAX_NCHANNELS=%s" % (ngroups, os.environ.get("NCCL_MAX_NCHANNELS"))) if world > 1 else None,
+                      "gather": ("%d group(s) per step behind their kernels, %s slabs, preallocated receive buffers, "
+                                 "NCCL_MAX_NCHANNELS=%s" % (ngroups, "REAL(4) output-ready" if g32 else "fp64",
+                                                            os.environ.get("NCCL_MAX_NCHANNELS"))) if do_gather else
+                                ("SKIPPED (--no-gather diagnostic)" if world > 1 else None),
                       "wet_fraction": m.wet_fraction}}
     if e2e:
         rec["e2e"] = e2e
@@ -683,7 +710,13 @@ def main():
                     help="wall-clock budget of this process: a sub-record (the other BASELINE configurations) is only started "
                          "while its estimated duration still fits")
     ap.add_argument("--no-subrecords", action="store_true", help="headline workload only")
-    ap.add_argument("--nccl-channels", type=int, default=4, help="NCCL_MAX_NCHANNELS for the slab gather (unless already set)")
+    ap.add_argument("--nccl-channels", type=int, default=0,
+                    help="NCCL_MAX_NCHANNELS for the slab gather (unless already set); 0 leaves NCCL's default")
+    ap.add_argument("--gather-dtype", default="f32", choices=["f32", "f64"],
+                    help="slabs gathered to rank 0: f32 = converted on the device to what the output file stores (REAL(4), plus "
+                         "the derived inp0 for cdfmoc); f64 = the raw fp64 slabs")
+    ap.add_argument("--gather-groups", type=int, default=4, help="the slabs of a step are gathered in this many groups")
+    ap.add_argument("--no-gather", action="store_true", help="diagnostic: skip the slab gather (the number is then NOT the job's)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -60,6 +60,9 @@ constexpr int kSigTabSlack = CDF_SIG_TAB_SLACK; // a new band starts this many b
 #ifndef CDF_SIG_PREFETCH_VA
 #define CDF_SIG_PREFETCH_VA 1   // V / area of window n+2 in flight during window n (0: only T / S of window n+1)
 #endif
+#ifndef CDF_SIG_UNROLL2
+#define CDF_SIG_UNROLL2 0       // 1: loop body twice with x / y exchanged (no rotation moves, twice the code)
+#endif
 #ifndef CDF_SIG_SEG_WIN
 #define CDF_SIG_SEG_WIN 6
 #endif
@@ -787,6 +790,20 @@ __global__ void __launch_bounds__(kSigThreads, kSigMinCtas) mocsig_eos_hist_scan
             sig_next_window(p, ws, a, &s_seg, j, k0, total, nwarps, wpr, lane, pol);
 #endif
             // x: window n (T / S in flight, transports in slot `slot`), a: window n+1 (V / area in flight)
+#if CDF_SIG_UNROLL2
+            // two copies of the loop body with the roles of x and y exchanged: no register moves to rotate the pipeline
+#pragma unroll 1
+            for (;;) {
+                if (!x.live) break;
+                sig_stage2<ISO>(p, a, y, pry, lane, pol);
+                sig_next_window(p, ws, a, &s_seg, j, k0, total, nwarps, wpr, lane, pol);
+                sig_stage3<NEUTRAL, ISO>(p, x, prx, hist, tab, st, s_poison, hsize, lane, pol);
+                if (!y.live) break;
+                sig_stage2<ISO>(p, a, x, prx, lane, pol);
+                sig_next_window(p, ws, a, &s_seg, j, k0, total, nwarps, wpr, lane, pol);
+                sig_stage3<NEUTRAL, ISO>(p, y, pry, hist, tab, st, s_poison, hsize, lane, pol);
+            }
+#else
             int slot = 0;
 #pragma unroll 1
             while (x.live) {
@@ -801,6 +818,7 @@ __global__ void __launch_bounds__(kSigThreads, kSigMinCtas) mocsig_eos_hist_scan
                 x = y;
                 slot ^= 1;
             }
+#endif
             sig_tab_flush(hist, tab, st, p.npat1, p.nbins, lane);
         }
         __syncthreads();
