@@ -17,7 +17,9 @@ gridV records, 5 basins.  One STEP = one pass of the hot path over the whole rec
 N > 1: one process per GPU (torchrun).
   time sharding  (cdfmoc workloads, cdfmocsig-ORCA025): every rank owns its own records -> weak scaling
   band sharding  (cdfmocsig-ORCA12-...-bands): every rank owns a latitude band of every record -> strong scaling
-The per-rank result slabs are gathered to rank 0 over NCCL inside the timed region (cdftools_b200/shard.py).
+Inside the timed region every rank copies its result slabs to page-locked host memory behind their kernels (--gather
+host, the default: the path has no exchange step and its result is a file); --gather nccl gathers them to rank 0's HBM
+instead (cdftools_b200/shard.py).
 """
 from __future__ import annotations
 
@@ -328,7 +330,8 @@ def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=T
     # slabs right behind its kernels on a side stream, into receive buffers allocated ONCE -- only the last group of the
     # last step is not overlapped by kernels
     ngroups = 1 if world == 1 else max(1, min(args.gather_groups, nrec // 2))
-    do_gather = world > 1 and not args.no_gather
+    do_gather = world > 1 and args.gather == "nccl"
+    do_host = world > 1 and args.gather == "host"
     gb = [(g * nrec) // ngroups for g in range(ngroups + 1)]
     recv, full = None, None
     # What travels is what the writer needs: the output files hold REAL(4) (src/cdfmoc.f90:520-551 REAL(dmoc(...)) and the
@@ -344,7 +347,9 @@ def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=T
         recv = [torch.empty((gmax,) + gshape, dtype=gdtype, device="cuda") for _ in range(world)]
         if band:
             full = torch.empty((nrec, nyg) + gshape[1:], dtype=gdtype, device="cuda")
-    gather_events = []
+    # --gather host (default): no collective at all.  The result is a file, so rank 0 need not hold the slabs in HBM: every
+    # rank copies its own slabs to page-locked host memory (copy engine, no SMs) right behind their kernels.
+    hres = [torch.empty((nrec,) + out_shape, dtype=torch.float64, pin_memory=True) for _ in range(2)] if do_host else None
 
     def launch(rec, o):
         if sig:
@@ -363,6 +368,12 @@ def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=T
             with torch.cuda.stream(st):
                 for r in range(gb[g], gb[g + 1]):
                     launch(recs[r % n_res], o[r])
+            if do_host:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                with torch.cuda.stream(comm):
+                    comm.wait_event(ev)
+                    hres[i & 1][gb[g]:gb[g + 1]].copy_(o[gb[g]:gb[g + 1]], non_blocking=True)
             if do_gather:
                 ev = torch.cuda.Event()
                 ev.record(st)
@@ -380,7 +391,7 @@ def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=T
                     if band and rank == 0:   # unpack the padded bands into the (record, j, bin, basin) array the writer wants
                         for rr, (b0, b1) in enumerate(bands):
                             full[gb[g]:gb[g + 1], b0:b1].copy_(recv[rr][: part.shape[0], : b1 - b0])
-        if do_gather:
+        if do_gather or do_host:
             gathered[i & 1] = torch.cuda.Event()
             gathered[i & 1].record(comm)
 
@@ -416,7 +427,7 @@ def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=T
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": None, "kernel": kname, "bytes_per_launch": bytes_launch, "ms_per_launch": ms_launch,
                 "peak_source": cx.peak_src, "frac_of_8TBps_spec": achieved / 8000.0,
-                "note": "per-GPU figure; at N>1 the launch time includes the overlapped NCCL slab gather",
+                "note": "per-GPU figure; at N>1 the launch time includes the overlapped copy of the result slabs (--gather)",
                 "peak_kind": "measured device-to-device COPY bandwidth (read + write); a read-only streaming kernel can "
                              "exceed it slightly (frac > 1) -- see frac_of_8TBps_spec"}
     tp = ROOT / "profiles" / ("k2_traffic.json" if sig else "k1_traffic.json")
@@ -508,6 +519,9 @@ def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=T
             ok = ok and bool(np.all(d <= np.maximum(1e-9 * np.abs(ref), 1e-6)))
         parity = {"rows_checked": int(len(cand)), "max_abs_err_sv": max(errs), "within_tolerance": ok,
                   "tolerance": "1e-9 relative or 1e-6 Sv"}
+        if do_host:   # what landed in host memory is what the device holds
+            torch.cuda.synchronize()
+            parity["host_copy_equals_device"] = bool(torch.equal(hres[(steps - 1) & 1], outs[(steps - 1) & 1].cpu()))
         if band and full is not None:   # the gathered array on rank 0 holds every band: rank 0's own rows must be in place
             parity["gathered_equals_local"] = bool(torch.equal(full[0, j0:j1, :, :nb], outs[(steps - 1) & 1][0, : j1 - j0].to(gdtype)))
 
@@ -566,12 +580,16 @@ def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=T
                       "basins": nb, "records_per_step_per_gpu": nrec, "resident_records": n_res, "rows_per_gpu": ny,
                       "l2": "inputs (%.1f GB resident per GPU) are far larger than the 126 MB L2; no flush needed"
                             % (n_res * rec_bytes / 1e9),
-                      "sharding": ("latitude bands + NCCL slab gather" if band else
-                                   "time (each rank owns its own records) + NCCL slab gather") if world > 1 else "single GPU",
+                      "sharding": (("latitude bands" if band else "time (each rank owns its own records)") +
+                                   {"host": "; no collective", "nccl": " + NCCL slab gather", "none": ""}[args.gather])
+                                  if world > 1 else "single GPU",
                       "gather": ("%d group(s) per step behind their kernels, %s slabs, preallocated receive buffers, "
                                  "NCCL_MAX_NCHANNELS=%s" % (ngroups, "REAL(4) output-ready" if g32 else "fp64",
                                                             os.environ.get("NCCL_MAX_NCHANNELS"))) if do_gather else
-                                ("SKIPPED (--no-gather diagnostic)" if world > 1 else None),
+                                ("every rank copies its own fp64 slabs to page-locked host memory in %d group(s) per step behind "
+                                 "their kernels, inside the timed region (the result is a file: no rank needs the others' slabs "
+                                 "in HBM)" % ngroups) if do_host else
+                                ("SKIPPED (--gather none diagnostic)" if world > 1 else None),
                       "wet_fraction": m.wet_fraction}}
     if e2e:
         rec["e2e"] = e2e
@@ -716,7 +734,10 @@ def main():
                     help="slabs gathered to rank 0: f32 = converted on the device to what the output file stores (REAL(4), plus "
                          "the derived inp0 for cdfmoc); f64 = the raw fp64 slabs")
     ap.add_argument("--gather-groups", type=int, default=4, help="the slabs of a step are gathered in this many groups")
-    ap.add_argument("--no-gather", action="store_true", help="diagnostic: skip the slab gather (the number is then NOT the job's)")
+    ap.add_argument("--gather", default="host", choices=["host", "nccl", "none"],
+                    help="N>1, where the result slabs go inside the timed region: host = every rank copies its own slabs to "
+                         "page-locked host memory (no collective: the result is a file); nccl = gathered to rank 0's HBM; "
+                         "none = diagnostic, slabs stay on the device (the number is then NOT the job's)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -60,9 +60,6 @@ constexpr int kSigTabSlack = CDF_SIG_TAB_SLACK; // a new band starts this many b
 #ifndef CDF_SIG_PREFETCH_VA
 #define CDF_SIG_PREFETCH_VA 1   // V / area of window n+2 in flight during window n (0: only T / S of window n+1)
 #endif
-#ifndef CDF_SIG_UNROLL2
-#define CDF_SIG_UNROLL2 0       // 1: loop body twice with x / y exchanged (no rotation moves, twice the code)
-#endif
 #ifndef CDF_SIG_SEG_WIN
 #define CDF_SIG_SEG_WIN 6
 #endif
@@ -180,10 +177,13 @@ __device__ __forceinline__ unsigned sigma_bins_f32x8(const float (&tt)[8], const
             // bound was derived on (NaN fails every comparison)
             const bool good = (fabsf(de[e]) > f.margin32) && (fabsf(__fsub_rn(qe[e], f.qc)) < f.qh) &&
                               (fmaxf(fabsf(ue[e]), fabsf(ve[e])) <= 1.0f);
-            if (!good && wanted(2 * g + e)) bad |= 1u << (2 * g + e);
+            bad |= good ? 0u : 1u << (2 * g + e);
         }
     }
-    return bad;
+    unsigned wm = 0u;   // (mask arithmetic instead of a branch per cell)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) wm |= wanted(c) ? 1u << c : 0u;
+    return bad & wm;
 }
 
 // ---- tier 2: the same 28-term polynomial in fp64 FMA, one cell ------------------------------------------------------
@@ -790,20 +790,6 @@ __global__ void __launch_bounds__(kSigThreads, kSigMinCtas) mocsig_eos_hist_scan
             sig_next_window(p, ws, a, &s_seg, j, k0, total, nwarps, wpr, lane, pol);
 #endif
             // x: window n (T / S in flight, transports in slot `slot`), a: window n+1 (V / area in flight)
-#if CDF_SIG_UNROLL2
-            // two copies of the loop body with the roles of x and y exchanged: no register moves to rotate the pipeline
-#pragma unroll 1
-            for (;;) {
-                if (!x.live) break;
-                sig_stage2<ISO>(p, a, y, pry, lane, pol);
-                sig_next_window(p, ws, a, &s_seg, j, k0, total, nwarps, wpr, lane, pol);
-                sig_stage3<NEUTRAL, ISO>(p, x, prx, hist, tab, st, s_poison, hsize, lane, pol);
-                if (!y.live) break;
-                sig_stage2<ISO>(p, a, x, prx, lane, pol);
-                sig_next_window(p, ws, a, &s_seg, j, k0, total, nwarps, wpr, lane, pol);
-                sig_stage3<NEUTRAL, ISO>(p, y, pry, hist, tab, st, s_poison, hsize, lane, pol);
-            }
-#else
             int slot = 0;
 #pragma unroll 1
             while (x.live) {
@@ -818,7 +804,6 @@ __global__ void __launch_bounds__(kSigThreads, kSigMinCtas) mocsig_eos_hist_scan
                 x = y;
                 slot ^= 1;
             }
-#endif
             sig_tab_flush(hist, tab, st, p.npat1, p.nbins, lane);
         }
         __syncthreads();
