@@ -301,3 +301,43 @@ def transig_record(e2u, e1v, e3u, e3v, zu, zv, zt, zs, pref, ds1min, ds1scalmin,
                                 _p(e1v, C.c_float), _p(e3u, C.c_float), _p(e3v, C.c_float), _p(zu, C.c_float),
                                 _p(zv, C.c_float), _p(zt, C.c_float), _p(zs, C.c_float), int(set_masks),
                                 _p(masku, C.c_uint8), _p(maskv, C.c_uint8), _p(dusig, C.c_double), _p(dvsig, C.c_double))
+
+
+def sigtrp_prepare(gdept1, e3w_a, e3w_b, zu, zspu, zs_a, zs_b, zsps, zt_a, zt_b, merid=False):
+    """Section slices (npk, npts) as read from the files -> dict(ddepu (npk+1, npts) f64, zu, zs, zt, zmask f32, nk, found).
+    src/cdfsigtrp.f90:428-460 (meridional) / :521-555 (zonal)."""
+    e3w_a, e3w_b, zu, zs_a, zs_b, zt_a, zt_b = (_f32(x) for x in (e3w_a, e3w_b, zu, zs_a, zs_b, zt_a, zt_b))
+    npk, npts = zu.shape
+    out = dict(ddepu=np.empty((npk + 1, npts), np.float64), zu=np.empty((npk, npts), np.float32),
+               zs=np.empty((npk, npts), np.float32), zt=np.empty((npk, npts), np.float32),
+               zmask=np.empty((npk, npts), np.float32))
+    found = C.c_int(0)
+    lib().oracle_sigtrp_prepare.restype = C.c_int
+    out["nk"] = lib().oracle_sigtrp_prepare(npts, npk, int(merid), C.c_float(gdept1), _p(e3w_a, C.c_float), _p(e3w_b, C.c_float),
+                                            _p(zu, C.c_float), C.c_float(zspu), _p(zs_a, C.c_float), _p(zs_b, C.c_float),
+                                            C.c_float(zsps), _p(zt_a, C.c_float), _p(zt_b, C.c_float),
+                                            _p(out["ddepu"], C.c_double), _p(out["zu"], C.c_float), _p(out["zs"], C.c_float),
+                                            _p(out["zt"], C.c_float), _p(out["zmask"], C.c_float), C.byref(found))
+    out["found"] = bool(found.value)
+    return out
+
+
+def sigtrp_section(eu, de3, ddepu, gdepw, zu, zt, zs, zmask, nk, dsigma_min, dsigma_max, nbins, mode=0, refdep=0.0,
+                   teos10=False, ddepw_brk=None):
+    """The compute part of one cdfsigtrp section (src/cdfsigtrp.f90:559-627) -> dict(dsigma_lev, dsig, dhiso, dwtrp,
+    dwtrpbin, dtrpbin).  mode 0 sigmai(refdep), 1 neutral density, 2 -temp."""
+    eu, de3, gdepw, zu, zt, zs, zmask = (_f32(x) for x in (eu, de3, gdepw, zu, zt, zs, zmask))
+    ddepu = np.ascontiguousarray(ddepu, np.float64)
+    npk, npts = zu.shape
+    assert ddepu.shape == (npk + 1, npts) and de3.shape == (npk, npts) and eu.shape == (npts,) and gdepw.shape == (npk,)
+    brk = None if ddepw_brk is None else _f32(ddepw_brk)
+    out = dict(dsigma_lev=np.empty(nbins + 1, np.float64), dsig=np.empty((nk + 1, npts), np.float64),
+               dhiso=np.empty((nbins + 1, npts), np.float64), dwtrp=np.empty((nbins + 1, npts), np.float64),
+               dwtrpbin=np.empty((nbins, npts), np.float64), dtrpbin=np.empty(nbins, np.float64))
+    lib().oracle_sigtrp_section(npts, npk, int(nk), _p(eu, C.c_float), _p(de3, C.c_float), _p(ddepu, C.c_double),
+                                _p(gdepw, C.c_float), None if brk is None else _p(brk, C.c_float), _p(zu, C.c_float),
+                                _p(zt, C.c_float), _p(zs, C.c_float), _p(zmask, C.c_float), int(mode), C.c_float(refdep),
+                                int(teos10), C.c_double(dsigma_min), C.c_double(dsigma_max), int(nbins),
+                                _p(out["dsigma_lev"], C.c_double), _p(out["dsig"], C.c_double), _p(out["dhiso"], C.c_double),
+                                _p(out["dwtrp"], C.c_double), _p(out["dwtrpbin"], C.c_double), _p(out["dtrpbin"], C.c_double))
+    return out

@@ -826,3 +826,149 @@ void oracle_transig_record(int nx, int ny, int nzm1, int teos10, float pref, int
     free(zdu);
     free(zdv);
 }
+
+/* ===================================================================================================================
+ * cdfsigtrp -- src/cdfsigtrp.f90: density-class transport across a zonal / meridional section.
+ * Section arrays are (npts, npk) in Fortran = [npk][npts] here.
+ * =================================================================================================================== */
+
+/* What the reference does with the section slices it has read, up to the density (:428-460 meridional, :521-555 zonal;
+ * the two branches differ only in which file columns are read -- and in one detail: the meridional branch masks the mean
+ * temperature (:460), the zonal one does not (:555)).
+ *   ddepu(ji,1) = gdept(1); ddepu(ji,jk) = ddepu(ji,jk-1) + MIN(e3w_a, e3w_b)     REAL(8) + REAL(4)     (:428-436 / :521-529)
+ *   zu: WHERE (zu == zspu) zu = 0                                                                      (:438-439 / :532-533)
+ *   zmask = 0 where either salinity is the missing value; zs = 0.5*(zs_a + zs_b)*zmask  (REAL(4))      (:442-446 / :536-541)
+ *   nk = first level whose SUM(zs(:,jk)) is zero (REAL(4) sequential sum)                               (:449-454 / :544-549)
+ *   zt = 0.5*(zt_a + zt_b) [* zmask]                                                                    (:458-460 / :553-555)
+ * ddepu has npk+1 rows, row 0 = 0 (the reference's ddepu(:,0), zeroed at :402).  Returns nk; the reference leaves nk
+ * undefined when no level is all land -- npk is returned then (*found = 0). */
+int oracle_sigtrp_prepare(int npts, int npk, int merid, float gdept1, const float *e3w_a, const float *e3w_b, const float *zu_in,
+                          float zspu, const float *zs_a, const float *zs_b, float zsps, const float *zt_a, const float *zt_b,
+                          double *ddepu, float *zu, float *zs, float *zt, float *zmask, int *found)
+{
+    for (int i = 0; i < npts; ++i) {
+        ddepu[i] = 0.0;
+        ddepu[(size_t)npts + i] = (double)gdept1;
+    }
+    for (int k = 1; k < npk; ++k)
+        for (int i = 0; i < npts; ++i) {
+            const size_t c = (size_t)k * npts + i;
+            const float m = e3w_a[c] < e3w_b[c] ? e3w_a[c] : e3w_b[c]; /* MIN(a,b): b unless a < b */
+            ddepu[(size_t)(k + 1) * npts + i] = ddepu[(size_t)k * npts + i] + (double)m;
+        }
+    for (size_t c = 0; c < (size_t)npk * npts; ++c) {
+        zu[c] = (zu_in[c] == zspu) ? 0.0f : zu_in[c];
+        zmask[c] = (zs_a[c] == zsps || zs_b[c] == zsps) ? 0.0f : 1.0f;
+        float a = zs_a[c] + zs_b[c];
+        a = 0.5f * a;
+        zs[c] = a * zmask[c];
+        float t = zt_a[c] + zt_b[c];
+        t = 0.5f * t;
+        zt[c] = merid ? t * zmask[c] : t;
+    }
+    int nk = npk;
+    *found = 0;
+    for (int k = 0; k < npk; ++k) {
+        float s = 0.0f;
+        for (int i = 0; i < npts; ++i) s = s + zs[(size_t)k * npts + i];
+        if (s == 0.0f) {
+            nk = k + 1;
+            *found = 1;
+            break;
+        }
+    }
+    return nk;
+}
+
+/* The compute part of one section (:559-627).
+ *   mode 0: dsig = sigmai(zt, zs, refdep)*zmask (sigma0 = sigmai at 0, eos.f90:630); 1: sigmantr*zmask; 2 (-temp): -zt*zmask
+ *   dsig(:,0) = dsig(:,1) - 1.e-4 ; land: dsig(jk) = dsig(jk-1) + 1.e-5  (REAL(4) literals, promoted)      (:569-578)
+ *   dhiso(ji,jiso): depth where the column's density first reaches dsigma_lev(jiso), linear in ddepu          (:581-601)
+ *   dwtrp(ji,jiso): transport from the surface down to dhiso (last box fractional)                            (:604-618)
+ *   dwtrpbin = dwtrp(jbin+1) - dwtrp(jbin); dtrpbin(jbin) = SUM over ji                                     (:621-627)
+ * gdepw: (npk) REAL(4); ddepw_brk != NULL (-brk): [npk][npts], the column's own w depths (:608).
+ * dsig has nk+1 rows (row 0 = the dummy layer); dhiso, dwtrp nbins+1 rows; dwtrpbin nbins rows; any of them may be NULL
+ * except dtrpbin. */
+void oracle_sigtrp_section(int npts, int npk, int nk, const float *eu, const float *de3, const double *ddepu, const float *gdepw,
+                           const float *ddepw_brk, const float *zu, const float *zt, const float *zs, const float *zmask, int mode,
+                           float refdep, int teos10, double dsigma_min, double dsigma_max, int nbins, double *dsigma_lev_out,
+                           double *dsig_out, double *dhiso_out, double *dwtrp_out, double *dwtrpbin_out, double *dtrpbin)
+{
+    const size_t n = (size_t)nk * npts;
+    double *dsig = (double *)calloc((size_t)(nk + 1) * npts, sizeof(double));
+    double *lev = (double *)malloc((size_t)(nbins + 1) * sizeof(double));
+    double *dhiso = (double *)malloc((size_t)(nbins + 1) * npts * sizeof(double));
+    double *dwtrp = (double *)malloc((size_t)(nbins + 1) * npts * sizeof(double));
+    const double dltsig = (dsigma_max - dsigma_min) / nbins;
+    lev[0] = dsigma_min;
+    for (int c = 2; c <= nbins + 1; ++c) lev[c - 1] = lev[0] + (c - 1) * dltsig; /* :355-359 */
+    if (mode == 2) {
+        for (size_t c = 0; c < n; ++c) {
+            const float m = -zt[c] * zmask[c];
+            dsig[npts + c] = (double)m;
+        }
+    } else {
+        if (mode == 1)
+            oracle_sigmantr(n, zt, zs, dsig + npts);
+        else
+            oracle_sigmai_dep(n, zt, zs, refdep, teos10, dsig + npts);
+        for (size_t c = 0; c < n; ++c) dsig[npts + c] = dsig[npts + c] * (double)zmask[c];
+    }
+    for (int i = 0; i < npts; ++i) dsig[i] = dsig[npts + i] - (double)1.e-4f;
+    for (int i = 0; i < npts; ++i)
+        for (int k = 1; k <= nk; ++k)
+            if (zmask[(size_t)(k - 1) * npts + i] == 0.0f) dsig[(size_t)k * npts + i] = dsig[(size_t)(k - 1) * npts + i] + (double)1.e-5f;
+#pragma omp parallel for schedule(static)
+    for (int iso = 0; iso <= nbins; ++iso) {
+        const double dsigma = lev[iso];
+        for (int i = 0; i < npts; ++i) {
+            double h = ddepu[(size_t)npk * npts + i];
+            for (int k = 1; k <= nk; ++k) {
+                const double d1 = dsig[(size_t)k * npts + i], d0 = dsig[(size_t)(k - 1) * npts + i];
+                if (d1 < dsigma) continue;
+                const double dalfa = (dsigma - d0) / (d1 - d0);
+                if (fabs(dalfa) > 1.1 || dalfa < 0.0) {
+                    h = 0.0;
+                } else {
+                    const double a = ddepu[(size_t)k * npts + i] * dalfa;
+                    const double b = (1.0 - dalfa) * ddepu[(size_t)(k - 1) * npts + i];
+                    h = a + b;
+                }
+                break;
+            }
+            dhiso[(size_t)iso * npts + i] = h;
+            double w = 0.0;
+            for (int k = 1; k <= nk - 1; ++k) {
+                const float gw1 = ddepw_brk ? ddepw_brk[(size_t)k * npts + i] : gdepw[k];             /* gdepw(jk+1) */
+                const float gw0 = ddepw_brk ? ddepw_brk[(size_t)(k - 1) * npts + i] : gdepw[k - 1];   /* gdepw(jk)   */
+                const double u = (double)zu[(size_t)(k - 1) * npts + i];
+                if ((double)gw1 < h) {
+                    const double t = (double)eu[i] * (double)de3[(size_t)(k - 1) * npts + i];
+                    w = w + t * u * 1.0;
+                } else {
+                    const double t = (double)eu[i] * (h - (double)gw0);
+                    w = w + t * u * 1.0;
+                    break;
+                }
+            }
+            dwtrp[(size_t)iso * npts + i] = w;
+        }
+    }
+    for (int b = 0; b < nbins; ++b) {
+        double s = 0.0;
+        for (int i = 0; i < npts; ++i) {
+            const double d = dwtrp[(size_t)(b + 1) * npts + i] - dwtrp[(size_t)b * npts + i];
+            if (dwtrpbin_out) dwtrpbin_out[(size_t)b * npts + i] = d;
+            s = s + d;
+        }
+        dtrpbin[b] = s;
+    }
+    if (dsigma_lev_out) memcpy(dsigma_lev_out, lev, (size_t)(nbins + 1) * sizeof(double));
+    if (dsig_out) memcpy(dsig_out, dsig, (size_t)(nk + 1) * npts * sizeof(double));
+    if (dhiso_out) memcpy(dhiso_out, dhiso, (size_t)(nbins + 1) * npts * sizeof(double));
+    if (dwtrp_out) memcpy(dwtrp_out, dwtrp, (size_t)(nbins + 1) * npts * sizeof(double));
+    free(dsig);
+    free(lev);
+    free(dhiso);
+    free(dwtrp);
+}
