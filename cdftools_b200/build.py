@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 HOST = CSRC / "host"
 HOST_TOOLS = {"cdfmoc_gpu": "cdfmoc_main.cpp", "cdfmocsig_gpu": "cdfmocsig_main.cpp", "cdfmhst_gpu": "cdfmhst_main.cpp",
               "cdfzonalsum_gpu": "cdfzonal_main.cpp", "cdfzonalmean_gpu": "cdfzonal_main.cpp",
-              "cdftransig_xy3d_gpu": "cdftransig_main.cpp", "nc3dump": "nc3dump_main.cpp"}
+              "cdftransig_xy3d_gpu": "cdftransig_main.cpp", "cdfsigtrp_gpu": "cdfsigtrp_main.cpp", "nc3dump": "nc3dump_main.cpp"}
 HOST_DEFINES = {"cdfzonalmean_gpu": ["-DZONAL_MEAN"]}
 
 

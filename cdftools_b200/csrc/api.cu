@@ -12,6 +12,7 @@
 #include "moc_decomp.cuh"
 #include "zonal_kernels.cuh"
 #include "transig_kernels.cuh"
+#include "sigtrp_kernels.cuh"
 #include "microbench.cuh"
 
 namespace cdfgpu {
@@ -416,6 +417,7 @@ static int cdfgpu_finalize_dev(void)
         cdfzonal_gpu_teardown();
         cdfmhst_gpu_teardown();
         cdftransig_gpu_teardown();
+        cdfsigtrp_gpu_teardown();
     }
     cudaStreamDestroy(g.s_compute);
     cudaStreamDestroy(g.s_copy);
@@ -867,4 +869,5 @@ static int cdfmoc_gpu_kernel_ms_dev(int slot, float *ms)
 #include "api_mocsig.inc"
 #include "api_zonal.inc"
 #include "api_transig.inc"
+#include "api_sigtrp.inc"
 #include "api_multi.inc"

@@ -284,7 +284,7 @@ inline void dummy_lat(const std::vector<float> &gphiv, int nx, int ny, std::vect
     for (int j = 0; j < ny; ++j) lat[j] = gphiv[(size_t)j * nx + i];
 }
 
-struct OutVar { std::string name, long_name, units; float valid_min, valid_max; float fill = 99999.f; std::string axis = "TZY"; };
+struct OutVar { std::string name, long_name, units; float valid_min, valid_max; float fill = 99999.f; std::string axis = "TZY"; std::string short_name = ""; };
 
 // create + createvar + putheadervar + putvar1d for the (t, depth|sigma, y, x=1) output files
 // (cdfio.F90:260-368,371-459,629-682,2290-2407; cdfmoc.f90:1019-1028,1182-1186; cdfmocsig.f90:502-510,576-581)
@@ -325,7 +325,7 @@ struct OutFile {
             w.put_att_float(id, "valid_min", v.valid_min);
             w.put_att_float(id, "valid_max", v.valid_max);
             w.put_att_text(id, "long_name", v.long_name);
-            w.put_att_text(id, "short_name", v.name);
+            w.put_att_text(id, "short_name", v.short_name.empty() ? v.name : v.short_name);
             w.put_att_int(id, "iweight", 1);
             w.put_att_text(id, "online_operation", "N/A");
             w.put_att_text(id, "axis", v.axis);

@@ -301,6 +301,31 @@ MODULE cdfgpu
      INTEGER(C_INT) FUNCTION cdftransig_gpu_teardown() BIND(C, NAME='cdftransig_gpu_teardown')
        IMPORT :: C_INT
      END FUNCTION cdftransig_gpu_teardown
+
+     ! ---- cdfsigtrp: one section, replaces src/cdfsigtrp.f90:559-627 -------------------------------------------
+     INTEGER(C_INT) FUNCTION cdfsigtrp_gpu_section(npts, npk, nk, eu, de3, ddepu, gdepw, ddepw_brk, zu, zt, zs, zmask, &
+          &   kmode, refdep, kteos10, dsigma_min, dsigma_max, nbins, dsigma_lev, dsig, dhiso, dwtrp, dwtrpbin,      &
+          &   dtrpbin) BIND(C, NAME='cdfsigtrp_gpu_section')
+       IMPORT :: C_INT, C_FLOAT, C_DOUBLE, C_PTR
+       INTEGER(C_INT), VALUE      :: npts, npk, nk, kmode, kteos10, nbins
+       REAL(C_FLOAT),  VALUE      :: refdep
+       REAL(C_DOUBLE), VALUE      :: dsigma_min, dsigma_max
+       REAL(C_FLOAT),  INTENT(in) :: eu(*), de3(*)               ! (npts), (npts,npk) REAL(4) copy of de3
+       REAL(C_DOUBLE), INTENT(in) :: ddepu(*)                    ! (npts,0:npk)
+       TYPE(C_PTR),    VALUE      :: gdepw, ddepw_brk            ! C_LOC of gdepw(npk) / REAL(4) ddepw(npts,npk), or C_NULL_PTR
+       REAL(C_FLOAT),  INTENT(in) :: zu(*), zt(*), zs(*), zmask(*)
+       TYPE(C_PTR),    VALUE      :: dsigma_lev, dsig, dhiso, dwtrp, dwtrpbin   ! C_LOC of the REAL(8) arrays, or C_NULL_PTR
+       REAL(C_DOUBLE), INTENT(out):: dtrpbin(*)                  ! (nbins)
+     END FUNCTION cdfsigtrp_gpu_section
+
+     INTEGER(C_INT) FUNCTION cdfsigtrp_gpu_kernel_ms(ms) BIND(C, NAME='cdfsigtrp_gpu_kernel_ms')
+       IMPORT :: C_INT, C_FLOAT
+       REAL(C_FLOAT), INTENT(out) :: ms
+     END FUNCTION cdfsigtrp_gpu_kernel_ms
+
+     INTEGER(C_INT) FUNCTION cdfsigtrp_gpu_teardown() BIND(C, NAME='cdfsigtrp_gpu_teardown')
+       IMPORT :: C_INT
+     END FUNCTION cdfsigtrp_gpu_teardown
   END INTERFACE
 
 CONTAINS

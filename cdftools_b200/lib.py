@@ -79,6 +79,10 @@ SIGNATURES = {
     "cdftransig_gpu_fetch": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cdftransig_gpu_kernel_ms": (C.c_int, [C.POINTER(C.c_float)]),
     "cdftransig_gpu_teardown": (C.c_int, []),
+    "cdfsigtrp_gpu_section": (C.c_int, [C.c_int] * 3 + [C.c_void_p] * 9 + [C.c_int, C.c_float, C.c_int, C.c_double, C.c_double, C.c_int]
+                              + [C.c_void_p] * 6),
+    "cdfsigtrp_gpu_kernel_ms": (C.c_int, [C.POINTER(C.c_float)]),
+    "cdfsigtrp_gpu_teardown": (C.c_int, []),
 }
 
 
@@ -522,3 +526,30 @@ def cdftransig_kernel_ms() -> float:
 
 def cdftransig_teardown():
     _chk(load().cdftransig_gpu_teardown(), "cdftransig_gpu_teardown")
+
+
+def cdfsigtrp_section(eu, de3, ddepu, gdepw, zu, zt, zs, zmask, nk, dsigma_min, dsigma_max, nbins, mode=0, refdep=0.0,
+                      teos10=False, ddepw_brk=None):
+    """One cdfsigtrp section on the device (src/cdfsigtrp.f90:559-627) -> dict(dsigma_lev, dsig, dhiso, dwtrp, dwtrpbin,
+    dtrpbin); arrays (npk, npts) C order = the reference's (npts,npk).  mode 0 sigmai(refdep), 1 neutral, 2 -temp."""
+    eu, de3, zu, zt, zs, zmask = (_c32(x) for x in (eu, de3, zu, zt, zs, zmask))
+    gdepw = _c32(gdepw) if gdepw is not None else None
+    brk = _c32(ddepw_brk) if ddepw_brk is not None else None
+    ddepu = np.ascontiguousarray(ddepu, np.float64)
+    npk, npts = zu.shape
+    assert ddepu.shape == (npk + 1, npts) and de3.shape == (npk, npts) and eu.shape == (npts,)
+    out = dict(dsigma_lev=np.empty(nbins + 1, np.float64), dsig=np.empty((nk + 1, npts), np.float64),
+               dhiso=np.empty((nbins + 1, npts), np.float64), dwtrp=np.empty((nbins + 1, npts), np.float64),
+               dwtrpbin=np.empty((nbins, npts), np.float64), dtrpbin=np.empty(nbins, np.float64))
+    _chk(load().cdfsigtrp_gpu_section(npts, npk, int(nk), _ptr(eu), _ptr(de3), _ptr(ddepu), _ptr(gdepw), _ptr(brk), _ptr(zu),
+                                      _ptr(zt), _ptr(zs), _ptr(zmask), int(mode), float(refdep), int(teos10), float(dsigma_min),
+                                      float(dsigma_max), int(nbins), _ptr(out["dsigma_lev"]), _ptr(out["dsig"]),
+                                      _ptr(out["dhiso"]), _ptr(out["dwtrp"]), _ptr(out["dwtrpbin"]), _ptr(out["dtrpbin"])),
+         "cdfsigtrp_gpu_section")
+    return out
+
+
+def cdfsigtrp_kernel_ms() -> float:
+    ms = C.c_float()
+    _chk(load().cdfsigtrp_gpu_kernel_ms(C.byref(ms)), "cdfsigtrp_gpu_kernel_ms")
+    return ms.value

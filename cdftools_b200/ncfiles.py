@@ -19,6 +19,16 @@ def _new(path, dims, version=2):
     return f
 
 
+def e3w_fields(m: synth.Mesh):
+    """(e3w_1d (nz), e3w (nz,ny,nx)) float32 for the synthetic mesh: the distance between T levels, thinned like e3v in the
+    partial bottom cells (cdfsigtrp reads them, src/cdfsigtrp.f90:418-425)."""
+    e3w_1d = np.empty(m.nz, np.float32)
+    e3w_1d[0] = 2.0 * m.gdept_1d[0]
+    e3w_1d[1:] = m.gdept_1d[1:] - m.gdept_1d[:-1]
+    ratio = np.clip(m.e3v_0 / m.e3t_1d[:, None, None].astype(np.float32), 0.05, 1.0)
+    return e3w_1d, (e3w_1d[:, None, None] * ratio).astype(np.float32)
+
+
 def write_mesh(m: synth.Mesh, outdir, with_basins=True, version=2, zgr="v3.6"):
     """zgr: the mesh_zgr flavour SetMeshZgrVersion tells apart (src/cdfio.F90:3310-3335): "v3.6" (e3v_0, *_1d), "v3.0"
     (e3v, gdepw_0 / gdept_0 / e3t_0 as (t,z) columns) or "v2.0" (e3v_ps, gdepw / gdept / e3t as (t,z,1,1))."""
@@ -34,6 +44,12 @@ def write_mesh(m: synth.Mesh, outdir, with_basins=True, version=2, zgr="v3.6"):
     f.close()
     f = _new(out / "mesh_zgr.nc", {"x": nx, "y": ny, "z": nz, "t": None, **({"x_a": 1, "y_a": 1} if zgr == "v2.0" else {})}, version)
     e3u = (m.e3v_0 * np.float32(1.01)).astype(np.float32)
+    e3w_1d, e3w = e3w_fields(m)
+    v = f.createVariable({"v3.6": "e3w_0", "v3.0": "e3w", "v2.0": "e3w_ps"}[zgr], "f", ("t", "z", "y", "x")); v[0] = e3w
+    if zgr == "v2.0":
+        v = f.createVariable("e3w", "f", ("t", "z", "y_a", "x_a")); v[0, :, 0, 0] = e3w_1d
+    else:
+        v = f.createVariable({"v3.6": "e3w_1d", "v3.0": "e3w_0"}[zgr], "f", ("t", "z")); v[0] = e3w_1d
     if zgr == "v3.6":
         v = f.createVariable("e3v_0", "f", ("t", "z", "y", "x")); v[0] = m.e3v_0
         v = f.createVariable("e3u_0", "f", ("t", "z", "y", "x")); v[0] = e3u

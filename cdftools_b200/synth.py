@@ -244,3 +244,49 @@ def setup_masks(mesh: Mesh, with_basins: bool = True) -> np.ndarray:
 def setup_e3v_masked(mesh: Mesh) -> np.ndarray:
     """e3v (nz,ny,nx) REAL(4) already multiplied by vmask, as get_e3v returns it (src/cdfmoc.f90:590-594)."""
     return (mesh.e3v_0 * mesh.vmask.astype(np.float32)).astype(np.float32)
+
+
+def make_section(npts: int, npk: int = 31, seed: int = SEED, spval: float = 0.0, noise: float = 0.05):
+    """Slices of a synthetic zonal / meridional section as cdfsigtrp reads them (src/cdfsigtrp.f90:406-460 / :505-555):
+    dict of (npk, npts) float32 arrays e3w_a, e3w_b, de3, zu, zs_a, zs_b, zt_a, zt_b, plus eu (npts), gdept, gdepw (npk).
+    A sloping sea floor with a sill, some dry columns, partial bottom cells; land carries `spval` in T, S and the velocity."""
+    rng = np.random.default_rng(seed + 7919 * npts + npk)
+    gdepw, gdept, e3t = (x.astype(np.float32) for x in vertical_grid(npk))
+    x = np.linspace(0.0, 1.0, npts)
+    # number of wet levels per column: a basin with a sill and shelves, never the last level
+    kbot = np.clip((npk - 2) * (0.15 + 0.85 * np.sin(np.pi * x) ** 2) * (1.0 - 0.35 * np.exp(-((x - 0.6) / 0.05) ** 2)), 0, npk - 2)
+    kbot = kbot.astype(int)
+    if npts > 8:
+        kbot[rng.integers(0, npts, max(1, npts // 40))] = 0   # islands
+    k = np.arange(npk)[:, None]
+
+    def wet_of(kb):
+        return k < kb[None, :]
+
+    kb_b = np.roll(kbot, -1) if npts > 1 else kbot
+    wet_a, wet_b = wet_of(kbot), wet_of(kb_b)
+    e3w = np.empty(npk, np.float32)
+    e3w[0] = 2.0 * gdept[0]
+    e3w[1:] = gdept[1:] - gdept[:-1]
+    part = (0.3 + 0.7 * rng.random((npk, npts))).astype(np.float32)   # partial cells
+    e3w_a = (e3w[:, None] * np.where(k == kbot[None, :] - 1, part, 1.0)).astype(np.float32)
+    e3w_b = (e3w[:, None] * np.where(k == kb_b[None, :] - 1, part[::-1], 1.0)).astype(np.float32)
+    de3 = (e3t[:, None] * np.where(k == np.minimum(kbot, kb_b)[None, :] - 1, part, 1.0)).astype(np.float32)
+    z = gdept[:, None].astype(np.float64)
+
+    def ts(shift):
+        t = 2.0 + 22.0 * np.exp(-z / 900.0) * (0.6 + 0.4 * np.cos(2.0 * np.pi * (x[None, :] + shift))) + noise * rng.standard_normal((npk, npts))
+        s = 34.6 + 1.0 * np.exp(-z / 500.0) * np.sin(2.0 * np.pi * x[None, :]) + 0.3 * (1 - np.exp(-z / 1500.0)) + 0.2 * noise * rng.standard_normal((npk, npts))
+        return t.astype(np.float32), s.astype(np.float32)
+
+    zt_a, zs_a = ts(0.0)
+    zt_b, zs_b = ts(0.01)
+    sp = np.float32(spval)
+    zt_a, zs_a = np.where(wet_a, zt_a, sp), np.where(wet_a, zs_a, sp)
+    zt_b, zs_b = np.where(wet_b, zt_b, sp), np.where(wet_b, zs_b, sp)
+    zu = (0.2 * np.exp(-z / 1200.0) * np.sin(6.0 * np.pi * x[None, :]) + 0.05 * rng.standard_normal((npk, npts))).astype(np.float32)
+    zu = np.where(wet_a & wet_b, zu, sp)
+    eu = (2.0e4 * (0.8 + 0.4 * rng.random(npts))).astype(np.float32)
+    f = np.float32
+    return dict(e3w_a=e3w_a, e3w_b=e3w_b, de3=de3, zu=zu.astype(f), zs_a=zs_a.astype(f), zs_b=zs_b.astype(f), zt_a=zt_a.astype(f),
+                zt_b=zt_b.astype(f), eu=eu, gdept=gdept, gdepw=gdepw)

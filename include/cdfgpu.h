@@ -232,6 +232,24 @@ int cdftransig_gpu_fetch(double *dusigsig, double *dvsigsig);
 int cdftransig_gpu_kernel_ms(float *ms); /* device time of the last record (both kernels) */
 int cdftransig_gpu_teardown(void);
 
+/* cdfsigtrp -- replaces the compute part of one section, src/cdfsigtrp.f90:559-627 (kernel K7): density of the section,
+ * depth of the nbins+1 class limits in every column, transport from the surface down to each of them, and the binned
+ * transports.  The host program keeps reading its section slices and the preparation of :428-555; arrays are the
+ * reference's own after that block, (npts,npk) Fortran order:
+ *   eu (npts) e1v or e2u; de3 (npts,npk) REAL(4) values of the reference's REAL(8) de3; ddepu (npts,0:npk) REAL(8);
+ *   gdepw (npk), or ddepw_brk (npts,npk) the column's own w depths with -brk (:608; then gdepw may be NULL);
+ *   zu, zt, zs, zmask (npts,npk) after the missing-value scrub / averaging; nk the number of levels used (:449-454).
+ *   mode 0: sigmai(zt,zs,refdep) (sigma0 when refdep = 0; teos10 selects the coefficient set), 1: sigmantr, 2: -temp.
+ *   dsigma_min, dsigma_max, nbins: class limits dsigma_lev(1:nbins+1) as at :355-359.
+ * Outputs (host, any but dtrpbin may be NULL): dsigma_lev (nbins+1); dsig (npts,0:nk); dhiso, dwtrp (npts,nbins+1);
+ * dwtrpbin (npts,nbins); dtrpbin (nbins) = SUM over the section, in m3/s (the caller divides by 1.d6). */
+int cdfsigtrp_gpu_section(int npts, int npk, int nk, const float *eu, const float *de3, const double *ddepu, const float *gdepw,
+                          const float *ddepw_brk, const float *zu, const float *zt, const float *zs, const float *zmask, int mode,
+                          float refdep, int teos10, double dsigma_min, double dsigma_max, int nbins, double *dsigma_lev,
+                          double *dsig, double *dhiso, double *dwtrp, double *dwtrpbin, double *dtrpbin);
+int cdfsigtrp_gpu_kernel_ms(float *ms); /* device time of the last section (four kernels) */
+int cdfsigtrp_gpu_teardown(void);
+
 #ifdef __cplusplus
 }
 #endif

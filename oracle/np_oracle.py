@@ -413,3 +413,86 @@ def transig_record(e2u, e1v, e3u, e3v, zu, zv, zt, zs, pref, ds1min, ds1scalmin,
             p = (e12.astype(f32) * (vel.astype(f32) * e3.astype(f32))).astype(np.float64) * 1.0
             ok = b >= 1
             acc[b[ok] - 1, jj[ok], ii[ok]] += p[ok]                          # one (bin, j, i) per cell: no duplicates
+
+
+# ---- cdfsigtrp (src/cdfsigtrp.f90) ---------------------------------------------------------------------------------
+def sigtrp_prepare(gdept1, e3w_a, e3w_b, zu, zspu, zs_a, zs_b, zsps, zt_a, zt_b, merid=False):
+    """:428-460 / :521-555, vectorised over the section; arrays (npk, npts) float32."""
+    f32 = np.float32
+    npk, npts = zu.shape
+    ddepu = np.zeros((npk + 1, npts), np.float64)
+    ddepu[1] = np.float64(f32(gdept1))
+    for k in range(1, npk):
+        ddepu[k + 1] = ddepu[k] + np.minimum(e3w_a[k], e3w_b[k]).astype(np.float64)
+    zu = np.where(zu == f32(zspu), f32(0), zu).astype(f32)
+    zmask = np.where((zs_a == f32(zsps)) | (zs_b == f32(zsps)), f32(0), f32(1)).astype(f32)
+    zs = (f32(0.5) * (zs_a + zs_b)) * zmask
+    zt = f32(0.5) * (zt_a + zt_b)
+    if merid:
+        zt = zt * zmask
+    nk, found = npk, False
+    for k in range(npk):
+        s = f32(0)
+        for v in zs[k]:
+            s = f32(s + v)
+        if s == 0:
+            nk, found = k + 1, True
+            break
+    return dict(ddepu=ddepu, zu=zu, zs=zs.astype(f32), zt=zt.astype(f32), zmask=zmask, nk=nk, found=found)
+
+
+def sigtrp_section(eu, de3, ddepu, gdepw, zu, zt, zs, zmask, nk, dsigma_min, dsigma_max, nbins, mode=0, refdep=0.0,
+                   teos10=False, ddepw_brk=None):
+    """:559-627, vectorised over the section, explicit loops over levels and class limits."""
+    f64 = np.float64
+    npk, npts = zu.shape
+    lev = np.empty(nbins + 1, f64)
+    dlt = (f64(dsigma_max) - f64(dsigma_min)) / f64(nbins)
+    lev[0] = dsigma_min
+    for c in range(2, nbins + 2):
+        lev[c - 1] = lev[0] + f64(c - 1) * dlt
+    dsig = np.zeros((nk + 1, npts), f64)
+    if mode == 2:
+        dsig[1:] = ((-zt[:nk]) * zmask[:nk]).astype(f64)
+    else:
+        d = sigmantr(zt[:nk], zs[:nk]) if mode == 1 else sigmai_dep(zt[:nk], zs[:nk], np.float32(refdep), teos10)
+        dsig[1:] = d * zmask[:nk].astype(f64)
+    dsig[0] = dsig[1] - f64(np.float32(1.e-4))
+    for k in range(1, nk + 1):
+        land = zmask[k - 1] == 0
+        dsig[k] = np.where(land, dsig[k - 1] + f64(np.float32(1.e-5)), dsig[k])
+    dhiso = np.empty((nbins + 1, npts), f64)
+    dwtrp = np.empty((nbins + 1, npts), f64)
+    e = eu.astype(f64)
+    with np.errstate(all="ignore"):
+        for iso in range(nbins + 1):
+            h = ddepu[npk].copy()
+            done = np.zeros(npts, bool)
+            for k in range(1, nk + 1):
+                hit = ~done & ~(dsig[k] < lev[iso])
+                if hit.any():
+                    dalfa = (lev[iso] - dsig[k - 1]) / (dsig[k] - dsig[k - 1])
+                    val = ddepu[k] * dalfa + (1.0 - dalfa) * ddepu[k - 1]
+                    val = np.where((np.abs(dalfa) > 1.1) | (dalfa < 0.0), 0.0, val)
+                    h = np.where(hit, val, h)
+                    done |= hit
+            dhiso[iso] = h
+            w = np.zeros(npts, f64)
+            done = np.zeros(npts, bool)
+            for k in range(1, nk):
+                gw1 = (ddepw_brk[k] if ddepw_brk is not None else np.full(npts, gdepw[k], np.float32)).astype(f64)
+                gw0 = (ddepw_brk[k - 1] if ddepw_brk is not None else np.full(npts, gdepw[k - 1], np.float32)).astype(f64)
+                u = zu[k - 1].astype(f64)
+                full = gw1 < h
+                add = np.where(full, (e * de3[k - 1].astype(f64)) * u, (e * (h - gw0)) * u)
+                w = np.where(done, w, w + add)
+                done |= ~full
+            dwtrp[iso] = w
+    dwtrpbin = dwtrp[1:] - dwtrp[:-1]
+    dtrpbin = np.empty(nbins, f64)
+    for b in range(nbins):
+        s = f64(0)
+        for v in dwtrpbin[b]:
+            s = s + v
+        dtrpbin[b] = s
+    return dict(dsigma_lev=lev, dsig=dsig, dhiso=dhiso, dwtrp=dwtrp, dwtrpbin=dwtrpbin, dtrpbin=dtrpbin)

@@ -11,7 +11,7 @@ ROOT = Path(__file__).resolve().parent.parent
 def _declared():
     txt = (ROOT / "include" / "cdfgpu.h").read_text()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return set(re.findall(r"\b(cdf(?:gpu|moc|mocsig|zonal|mhst|transig)_\w+)\s*\(", txt))
+    return set(re.findall(r"\b(cdf(?:gpu|moc|mocsig|zonal|mhst|transig|sigtrp)_\w+)\s*\(", txt))
 
 
 def test_library_builds_and_exports_every_declared_symbol():

@@ -363,3 +363,102 @@ def test_cdfmoc_cli_nam_cdf_names_and_nc4(tools, oracle_mod, tmp_path):
     (tmp_path / "nam_cdf_names").unlink()
     r = subprocess.run([tools["cdfmoc_gpu"], "-v", "gridV.nc"], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 99 and "mesh_hgr.nc is missing" in r.stdout
+
+
+def _sigtrp_expected(oracle_mod, m, u, v, t, s, sec, smin, smax, nbins, spval=0.0, **kw):
+    """What cdfsigtrp computes for one section from the arrays the files hold (src/cdfsigtrp.f90:404-627)."""
+    imin, imax, jmin, jmax = sec
+    e3w_1d, e3w = ncfiles.e3w_fields(m)
+    e2u = (m.e1u * np.float32(0.9)).astype(np.float32)
+    e3u = (m.e3v_0 * np.float32(1.01)).astype(np.float32)
+    if imin == imax:   # meridional: rows jmin+1 .. jmax at column imin, T / S also at imin+1
+        rows, i0 = slice(jmin, jmax), imin - 1
+        cut = lambda a, i: np.ascontiguousarray(a[:, rows, i])
+        eu, de3 = e2u[rows, i0].copy(), cut(e3u, i0)
+        raw = dict(e3w_a=cut(e3w, i0), e3w_b=cut(e3w, i0 + 1), zu=cut(u, i0), zs_a=cut(s, i0), zs_b=cut(s, i0 + 1), zt_a=cut(t, i0),
+                   zt_b=cut(t, i0 + 1))
+        merid = True
+    else:              # zonal: columns imin+1 .. imax at row jmin, T / S also at jmin+1; e1v starts at imin (as the reference reads it)
+        cols, j0 = slice(imin, imax), jmin - 1
+        cut = lambda a, j: np.ascontiguousarray(a[:, j, cols])
+        eu, de3 = m.e1v[j0, imin - 1:imax - 1].copy(), cut(m.e3v_0, j0)
+        raw = dict(e3w_a=cut(e3w, j0), e3w_b=cut(e3w, j0 + 1), zu=cut(v, j0), zs_a=cut(s, j0), zs_b=cut(s, j0 + 1), zt_a=cut(t, j0),
+                   zt_b=cut(t, j0 + 1))
+        merid = False
+    p = oracle_mod.sigtrp_prepare(m.gdept_1d[0], raw["e3w_a"], raw["e3w_b"], raw["zu"], spval, raw["zs_a"], raw["zs_b"], spval, raw["zt_a"],
+                                  raw["zt_b"], merid=merid)
+    o = oracle_mod.sigtrp_section(eu, de3, p["ddepu"], m.gdepw_1d.astype(np.float32), p["zu"], p["zt"], p["zs"], p["zmask"], p["nk"], smin,
+                                  smax, nbins, **kw)
+    return p, o
+
+
+@pytest.mark.parametrize("args,kw,lims", [([], {}, (23.0, 28.5, 22)), (["-refdep", "2000"], dict(refdep=2000.0), (31.0, 37.5, 26)),
+                                         (["-neutral"], dict(mode=1), (23.0, 28.5, 11)), (["-temp"], dict(mode=2), (0.0, 26.0, 13))])
+def test_cdfsigtrp_cli_matches_oracle(tools, oracle_mod, tmp_path, args, kw, lims):
+    """cdfsigtrp_gpu on a zonal, a meridional and an oblique (skipped) section: trpsig.txt and <section>_trpsig.nc against
+    the oracle fed with the slices the reference would read (e1v from imin, data from imin+1: src/cdfsigtrp.f90:497,516)."""
+    m = synth.make_mesh("SMALL")
+    ncfiles.write_mesh(m, tmp_path)
+    u = ncfiles.write_gridu(m, tmp_path / "SYN_y2026_gridU.nc", 1)[0]
+    v = ncfiles.write_gridv(m, tmp_path / "SYN_y2026_gridV.nc", 1)[0]
+    t, s = ncfiles.write_gridt(m, tmp_path / "SYN_y2026_gridT.nc", 1)[0]
+    secs = {"01_zonal": (20, 150, 17, 17), "02_merid": (60, 60, 4, 33), "03_oblique": (10, 20, 5, 9)}
+    (tmp_path / "dens_section.dat").write_text(
+        "01_zonal zon Zonal_line\n20 150 17 17\n02_merid\n60 60 4 33\n03_oblique obl\n10 20 5 9\nEOF\n")
+    smin, smax, nbins = lims
+    out = _run(tools["cdfsigtrp_gpu"], ["-t", "SYN_y2026_gridT.nc", "-u", "SYN_y2026_gridU.nc", "-v", "SYN_y2026_gridV.nc", "-smin", str(smin),
+                                        "-smax", str(smax), "-nbins", str(nbins)] + args, tmp_path)
+    assert "03_oblique is neither zonal nor meridional" in out
+    temp = kw.get("mode") == 2
+    lo, hi = (-smax, -smin) if temp else (smin, smax)   # -temp: sign changed, limits swapped (:303-308)
+    txt = (tmp_path / "trpsig.txt").read_text().splitlines()
+    assert txt[0] == "# SYN_y2026" and txt[1].startswith("#  sigma  ") and "01_zonal" in txt[1] and len(txt) == 2 + nbins
+    for name, sec in secs.items():
+        if name == "03_oblique":
+            continue
+        p, o = _sigtrp_expected(oracle_mod, m, u, v, t, s, sec, lo, hi, nbins, **kw)
+        assert ("NK =  %d" % p["nk"] if sec[0] == sec[1] else "JMM nk   %d" % p["nk"]) in out
+        f = netcdf_file(str(tmp_path / (name + ("_trptemp.nc" if temp else "_trpsig.nc"))), "r", mmap=False)
+        vn = ("temptrp" if temp else "sigtrp") + ("_zon" if name == "01_zonal" else "")
+        assert f.variables[vn].shape == (1, nbins, 1, 1) and f.variables[vn].units == b"Sv" and f.variables[vn].axis == b"ZT"
+        assert f.variables[vn].short_name == (b"temptrp" if temp else b"sigtrp")
+        if name == "01_zonal":
+            assert f.variables[vn].long_name.startswith(b"Zonal_line_transport in ")
+        assert np.array_equal(f.variables["temp_class" if temp else "sigma_class"][0, :, 0, 0], o["dsigma_lev"][:nbins].astype(np.float32))
+        assert np.array_equal(f.variables["levels"][:], o["dsigma_lev"][:nbins].astype(np.float32))
+        got, want = f.variables[vn][0, :, 0, 0], (o["dtrpbin"] / 1.e6).astype(np.float32)
+        assert np.any(want != 0)
+        assert np.array_equal(got, want), (name, np.abs(got - want).max())
+        assert np.isclose(f.variables["time_counter"][0], 216000.0)
+        f.close()
+        col = 0 if name == "01_zonal" else 1
+        for b in range(nbins):   # FORMAT(f9.4, 20e16.7)
+            line = txt[2 + b]
+            assert float(line[:9]) == pytest.approx(o["dsigma_lev"][b], abs=5e-5)
+            field = line[9 + 16 * col: 9 + 16 * (col + 1)]
+            assert field.strip().startswith(("0.", "-0.")) and "E" in field
+            assert float(field) == pytest.approx(o["dtrpbin"][b], rel=6e-7, abs=1e-30)   # seven digits after "0."
+
+
+def test_cdfsigtrp_cli_full_step_and_errors(tools, oracle_mod, tmp_path):
+    m = synth.make_mesh("ODD")
+    ncfiles.write_mesh(m, tmp_path)
+    ncfiles.write_gridu(m, tmp_path / "gridU.nc", 1)
+    v = ncfiles.write_gridv(m, tmp_path / "gridV.nc", 1)[0]
+    t, s = ncfiles.write_gridt(m, tmp_path / "x_gridT.nc", 1)[0]
+    (tmp_path / "sec.dat").write_text("line\n3 30 4 4\nEOF\n")
+    base = ["-t", "x_gridT.nc", "-u", "gridU.nc", "-v", "gridV.nc", "-smin", "23", "-smax", "28.5", "-nbins", "9", "-section", "sec.dat"]
+    _run(tools["cdfsigtrp_gpu"], base + ["-full"], tmp_path)
+    e3w_1d, _ = ncfiles.e3w_fields(m)
+    cols = slice(3, 30)
+    cut = lambda a, j: np.ascontiguousarray(a[:, j, cols])
+    full = lambda a: np.repeat(a.astype(np.float32)[:, None], 27, axis=1)
+    p = oracle_mod.sigtrp_prepare(m.gdept_1d[0], full(e3w_1d), full(e3w_1d), cut(v, 3), 0.0, cut(s, 3), cut(s, 4), 0.0, cut(t, 3), cut(t, 4))
+    o = oracle_mod.sigtrp_section(m.e1v[3, 2:29].copy(), full(m.e3t_1d), p["ddepu"], m.gdepw_1d.astype(np.float32), p["zu"], p["zt"], p["zs"],
+                                  p["zmask"], p["nk"], 23.0, 28.5, 9)
+    f = netcdf_file(str(tmp_path / "line_trpsig.nc"), "r", mmap=False)
+    assert np.array_equal(f.variables["sigtrp"][0, :, 0, 0], (o["dtrpbin"] / 1.e6).astype(np.float32))
+    f.close()
+    for bad, code in ((base[:-4], 99), (base + ["-xtra"], 99), (base + ["-bogus"], 99), (["-t", "nofile.nc"] + base[2:], 99)):
+        r = subprocess.run([tools["cdfsigtrp_gpu"]] + bad, capture_output=True, text=True, cwd=tmp_path, timeout=120)
+        assert r.returncode == code, (bad, r.stdout)
