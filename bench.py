@@ -657,6 +657,75 @@ def e2e_files(cx: Ctx, nrec=12):
                     "pinned -> H2D -> GPU byte swap -> K1 -> D2H -> moc.nc; files on tmpfs"}
 
 
+def siblings(cx: Ctx):
+    """The sibling kernels of SURVEY.md section 8 (f3) on one ORCA025 record each, through the C ABI with host arrays: device
+    time of the kernels (events inside the library), algorithmic bytes / that time against the HBM peak.  K7 (cdfsigtrp) is a
+    section, not a field: device time, wall time through the ABI, and equality with the oracle's result."""
+    from cdftools_b200 import synth
+    lib, peak = cx.lib, cx.hbm_peak
+    m = synth.make_mesh("ORCA025")
+    nk, ny, nx = m.nz - 1, m.ny, m.nx
+    n3 = nk * ny * nx
+    rng = np.random.default_rng(11)
+    out = {}
+
+    def rec(name, ms, nbytes, note):
+        out[name] = {"ms_per_record": ms, "bytes_per_record": int(nbytes), "achieved_gbs": nbytes / (ms * 1e-3) / 1e9,
+                     "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "note": note}
+
+    zv = synth.make_v_record(m, 3)[:nk].astype(np.float32)
+    msk = m.tmask[:nk].astype(np.float32)
+    zm = np.stack([msk[0], m.tmaskatl, np.minimum(1.0, m.tmaskind + m.tmaskpac), m.tmaskind, m.tmaskpac], -1).astype(np.float32)
+    e2 = (m.e1v * np.float32(0.75)).astype(np.float32)
+    shape = lib.cdfzonal_setup(m.e1v, e2, zm, msk)
+    for _ in range(2):
+        lib.cdfzonal_sum(zv, shape)
+    rec("K4_cdfzonalsum", lib.cdfzonal_kernel_ms(), n3 * 8, "zv + level mask, 5 basins (src/cdfzonalsum.f90:309-322)")
+    for _ in range(2):
+        lib.cdfzonal_mean(zv, shape)
+    rec("K4_cdfzonalmean", lib.cdfzonal_kernel_ms(), n3 * 8, "src/cdfzonalmean.f90:312-344")
+    lib.cdfzonal_teardown()
+    dims = lib.cdfmhst_setup(m.e1v, m.e3v_0, m.vmask[0].astype(np.float32), m.tmaskatl, m.tmaskpac, m.tmaskind)
+    zvt = (synth.make_v_record(m, 4) * 10.0).astype(np.float32)
+    zvs = (synth.make_v_record(m, 5) * 35.0).astype(np.float32)
+    for _ in range(2):
+        lib.cdfmhst_record(zvt, zvs, dims)
+    rec("K5_cdfmhst", lib.cdfmhst_kernel_ms(), m.nz * ny * nx * 12, "vomevt + vomevs + e3v (src/cdfmhst.f90:303-366)")
+    lib.cdfmhst_teardown()
+    pref, nb, smin, scal, zoom, smn = lib.TRANSIG_CODES["1000"]
+    _, _, itab, scm = lib.transig_bins(nb, smin, scal, zoom, smn)
+    e2u = (m.e1u * np.float32(0.9)).astype(np.float32)
+    e3u = (m.e3v_0 * np.float32(1.01)).astype(np.float32)
+    lib.cdftransig_setup(e2u, m.e1v, e3u[:nk], m.e3v_0[:nk], m.nz, nb, pref, smin, scm, itab)
+    zu = (synth.make_v_record(m, 6)[:nk] * m.umask[:nk]).astype(np.float32)
+    zt, zs = (x[:nk] for x in synth.make_ts_record(m, 0))
+    for i in range(2):
+        lib.cdftransig_record(zu, zv * m.vmask[:nk], zt, zs, i == 0)
+    rec("K6_cdftransig_xy3d", lib.cdftransig_kernel_ms(), n3 * 80, "src/cdftransig_xy3d.f90:396-461, 93 classes; about 80 bytes per "
+        "level-cell (densities written and re-read, velocities, metrics, masks, two scattered fp64 read-modify-writes)")
+    lib.cdftransig_teardown()
+    # K7: a long section (an ORCA12 line across the Atlantic) in 100 classes
+    import oracle
+    sec = synth.make_section(4000, 75, seed=5)
+    p = oracle.sigtrp_prepare(sec["gdept"][0], sec["e3w_a"], sec["e3w_b"], sec["zu"], 0.0, sec["zs_a"], sec["zs_b"], 0.0, sec["zt_a"],
+                              sec["zt_b"])
+    a = (sec["eu"], sec["de3"], p["ddepu"], sec["gdepw"], p["zu"], p["zt"], p["zs"], p["zmask"], p["nk"], 23.0, 28.5, 100)
+    lib.cdfsigtrp_section(*a)
+    t0 = time.perf_counter()
+    got = lib.cdfsigtrp_section(*a)
+    t_abi = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ref = oracle.sigtrp_section(*a)
+    t_cpu = time.perf_counter() - t0
+    out["K7_cdfsigtrp"] = {"section": "4000 columns x 75 levels, 100 classes", "kernels_ms": lib.cdfsigtrp_kernel_ms(),
+                           "abi_call_ms": t_abi * 1e3, "oracle_ms": t_cpu * 1e3, "oracle_threads": oracle.num_threads(),
+                           "equals_oracle": bool(all(np.array_equal(got[k], ref[k], equal_nan=True) for k in ref)),
+                           "note": "src/cdfsigtrp.f90:559-627; O(columns x classes x levels) latency-bound work, not a roofline item "
+                                   "(the ABI call copies every intermediate array back: dhiso, dwtrp, dwtrpbin)"}
+    out["parity"] = "tests/test_gpu_siblings.py, tests/test_transig.py, tests/test_sigtrp.py (bit-exact classes; sums within 1e-12 relative)"
+    return out
+
+
 def run_ours(args):
     cx = Ctx(args)
     rank, world = cx.rank, cx.world
@@ -701,6 +770,7 @@ def run_ours(args):
             return r
         sub("k2_config3", k2, 60)
         sub("e2e_files", lambda: e2e_files(cx), 90)
+        sub("siblings", lambda: siblings(cx), 60)
     else:
         sub("config4", lambda: measure(cx, "cdfmoc-ORCA12-L75-46rec-5basins", steps=3, warmup=3, nrec=6, do_e2e=False), 240)
         sub("config5", lambda: measure(cx, "cdfmocsig-ORCA12-L75-sigma2-158bins-8rec-bands", steps=3, warmup=3, nrec=4,

@@ -312,10 +312,13 @@ MODULE cdfgpu
        REAL(C_DOUBLE), VALUE      :: dsigma_min, dsigma_max
        REAL(C_FLOAT),  INTENT(in) :: eu(*), de3(*)               ! (npts), (npts,npk) REAL(4) copy of de3
        REAL(C_DOUBLE), INTENT(in) :: ddepu(*)                    ! (npts,0:npk)
-       TYPE(C_PTR),    VALUE      :: gdepw, ddepw_brk            ! C_LOC of gdepw(npk) / REAL(4) ddepw(npts,npk), or C_NULL_PTR
+       REAL(C_FLOAT),  INTENT(in) :: gdepw(*)                    ! (npk)
+       TYPE(C_PTR),    VALUE      :: ddepw_brk                   ! C_LOC of a REAL(4) (npts,npk) copy of ddepw (-brk), else C_NULL_PTR
        REAL(C_FLOAT),  INTENT(in) :: zu(*), zt(*), zs(*), zmask(*)
-       TYPE(C_PTR),    VALUE      :: dsigma_lev, dsig, dhiso, dwtrp, dwtrpbin   ! C_LOC of the REAL(8) arrays, or C_NULL_PTR
-       REAL(C_DOUBLE), INTENT(out):: dtrpbin(*)                  ! (nbins)
+       REAL(C_DOUBLE), INTENT(out):: dsigma_lev(*)               ! (nbins+1)
+       REAL(C_DOUBLE), INTENT(out):: dsig(*)                     ! (npts,0:nk): the first nk+1 rows of dsig(npts,0:npk)
+       REAL(C_DOUBLE), INTENT(out):: dhiso(*), dwtrp(*)          ! (npts,nbins+1)
+       REAL(C_DOUBLE), INTENT(out):: dwtrpbin(*), dtrpbin(*)     ! (npts,nbins), (nbins)
      END FUNCTION cdfsigtrp_gpu_section
 
      INTEGER(C_INT) FUNCTION cdfsigtrp_gpu_kernel_ms(ms) BIND(C, NAME='cdfsigtrp_gpu_kernel_ms')

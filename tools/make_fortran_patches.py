@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Generates cdftools_b200/fortran/patches/{cdfmoc,cdfmocsig}.f90.patch: the call-site changes a CDFTOOLS maintainer applies
+"""Generates cdftools_b200/fortran/patches/{cdfmoc,cdfmocsig,cdfsigtrp}.f90.patch: the call-site changes a CDFTOOLS maintainer applies
 to the reference drivers so that the hot loop nests run on the GPU behind libcdfgpu's C ABI.
 
     python tools/make_fortran_patches.py /path/to/CDFTOOLS        # default /root/reference
@@ -248,9 +248,54 @@ def patch_cdfmocsig(src):
     return "\n".join(L)
 
 
+def patch_cdfsigtrp(src):
+    L = src.split("\n")
+    insert_after(L, lambda l: l.strip().startswith("USE eos"), [
+        "  USE cdfgpu          ! ISO_C_BINDING interface of libcdfgpu.so (the B200 hot path)",
+    ])
+    insert_after(L, lambda l: l.startswith("  LOGICAL") and "ll_teos10" in l, [
+        "",
+        "  ! GPU hot path : REAL(4) copies the library takes, per-section result",
+        "  INTEGER(KIND=4)                             :: imode, iteos10        ! density mode, TEOS10 flag",
+        "  REAL(KIND=4), DIMENSION(:,:), ALLOCATABLE         :: zde3            ! de3 holds REAL(4) file values",
+        "  REAL(KIND=4), DIMENSION(:,:), ALLOCATABLE, TARGET :: zdepw           ! -brk : w depths of every column",
+        "  REAL(KIND=8), DIMENSION(:),   ALLOCATABLE         :: dtrpbin_sec     ! binned transport of the section",
+        "  TYPE(C_PTR)                                       :: pdepw",
+    ])
+    insert_after(L, lambda l: l.strip() == "!! *  Main loop on sections", [
+        "  CALL cdfgpu_check( cdfgpu_init(-1, 1), 'cdfgpu_init' )",
+        "  ALLOCATE ( dtrpbin_sec(nbins) )",
+    ])
+    i0, i1 = between(L, lambda l: l.strip() == "! compute density only for wet points",
+                     lambda l: l.strip() == "! output of the code for 1 section")
+    gpu = '''     ! ---- GPU hot path (replaces the density, isopycnal depth, cumulated and binned transport loop nests) ----
+     ALLOCATE ( zde3(npts,npk), zdepw(npts,npk) )
+     zde3(:,:) = REAL(de3(:,:))
+     pdepw     = C_NULL_PTR
+     IF ( lbrk ) THEN                        ! in broken line gdepw is not available as 1d array
+        zdepw(:,:) = REAL(ddepw(:,1:npk))
+        pdepw      = C_LOC(zdepw)
+     ENDIF
+     imode = 0                               ! sigmai(refdep) ; sigma0 when refdep = 0
+     IF ( lntr           ) imode = 1         ! neutral density
+     IF ( refdep == -10. ) imode = 2         ! -temp
+     iteos10 = 0 ; IF ( ll_teos10 ) iteos10 = 1
+     CALL cdfgpu_check( cdfsigtrp_gpu_section(npts, npk, nk, eu, zde3, ddepu, gdepw, pdepw, zu, zt, zs, zmask,   &
+          &   imode, refdep, iteos10, dsigma_min, dsigma_max, nbins, dsigma_lev, dsig, dhiso, dwtrp, dwtrpbin,   &
+          &   dtrpbin_sec), 'cdfsigtrp_gpu_section' )
+     dtrpbin(jsec,:) = dtrpbin_sec(:)
+     DEALLOCATE ( zde3, zdepw )
+'''.split("\n")
+    L[i0:i1] = gpu
+    insert_after(L, lambda l: l.strip() == "END DO   ! next section", [
+        "  CALL cdfgpu_check( cdfgpu_finalize(), 'cdfgpu_finalize' )",
+    ])
+    return "\n".join(L)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
-    for name, fn in (("cdfmoc.f90", patch_cdfmoc), ("cdfmocsig.f90", patch_cdfmocsig)):
+    for name, fn in (("cdfmoc.f90", patch_cdfmoc), ("cdfmocsig.f90", patch_cdfmocsig), ("cdfsigtrp.f90", patch_cdfsigtrp)):
         a = (REF / name).read_text()
         b = fn(a)
         d = difflib.unified_diff(a.split("\n"), b.split("\n"), "a/src/" + name, "b/src/" + name, lineterm="", n=3)
