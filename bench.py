@@ -264,8 +264,9 @@ class Ctx:
 
 
 def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=True, do_smooth=True, do_cpu=False,
-            clocks=None):
-    """One workload on this process' GPU (all ranks call it together): kernel phase with the NCCL slab gather, roofline,
+            clocks=None, gather=None):
+    """One workload on this process' GPU (all ranks call it together): kernel phase with the result slabs leaving the device
+    (--gather), roofline,
     optional end-to-end pipeline, parity spot check against the oracle on rank 0.  Returns the JSON-able record (rank 0
     holds the meaningful one)."""
     torch, dist, lib, shard, args = cx.torch, cx.dist, cx.lib, cx.shard, cx.args
@@ -330,8 +331,9 @@ def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=T
     # slabs right behind its kernels on a side stream, into receive buffers allocated ONCE -- only the last group of the
     # last step is not overlapped by kernels
     ngroups = 1 if world == 1 else max(1, min(args.gather_groups, nrec // 2))
-    do_gather = world > 1 and args.gather == "nccl"
-    do_host = world > 1 and args.gather == "host"
+    gather = gather or args.gather
+    do_gather = world > 1 and gather == "nccl"
+    do_host = world > 1 and gather == "host"
     gb = [(g * nrec) // ngroups for g in range(ngroups + 1)]
     recv, full = None, None
     # What travels is what the writer needs: the output files hold REAL(4) (src/cdfmoc.f90:520-551 REAL(dmoc(...)) and the
@@ -581,7 +583,7 @@ def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=T
                       "l2": "inputs (%.1f GB resident per GPU) are far larger than the 126 MB L2; no flush needed"
                             % (n_res * rec_bytes / 1e9),
                       "sharding": (("latitude bands" if band else "time (each rank owns its own records)") +
-                                   {"host": "; no collective", "nccl": " + NCCL slab gather", "none": ""}[args.gather])
+                                   {"host": "; no collective", "nccl": " + NCCL slab gather", "none": ""}[gather])
                                   if world > 1 else "single GPU",
                       "gather": ("%d group(s) per step behind their kernels, %s slabs, preallocated receive buffers, "
                                  "NCCL_MAX_NCHANNELS=%s" % (ngroups, "REAL(4) output-ready" if g32 else "fp64",
@@ -646,6 +648,7 @@ def e2e_files(cx: Ctx, nrec=12):
         size = (Path(d) / "gridV.nc").stat().st_size
         env = dict(os.environ, CDFGPU_DEVICE=str(cx.local))
         subprocess.run([tools["cdfmoc_gpu"], "-v", "gridV.nc"], cwd=d, check=True, capture_output=True, env=env)   # warm page cache
+        env["CDFGPU_TIMING"] = "1"   # phase times on stderr
         t0 = time.perf_counter()
         r = subprocess.run([tools["cdfmoc_gpu"], "-v", "gridV.nc"], cwd=d, check=True, capture_output=True, env=env, text=True)
         dt = time.perf_counter() - t0
@@ -775,6 +778,9 @@ def run_ours(args):
         sub("config4", lambda: measure(cx, "cdfmoc-ORCA12-L75-46rec-5basins", steps=3, warmup=3, nrec=6, do_e2e=False), 240)
         sub("config5", lambda: measure(cx, "cdfmocsig-ORCA12-L75-sigma2-158bins-8rec-bands", steps=3, warmup=3, nrec=4,
                                        do_e2e=False), 120)
+        if args.gather != "nccl":   # the headline workload once more with the slabs gathered to rank 0's HBM over NCCL / NVLink
+            sub("gather_nccl", lambda: measure(cx, args.workload, steps=min(args.steps, 5), warmup=3, do_e2e=False, do_smooth=False,
+                                               gather="nccl"), 60)
     if rank == 0:
         line["sub_records"] = subs
         line["wall_s"] = cx.elapsed()
