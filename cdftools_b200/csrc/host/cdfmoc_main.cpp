@@ -210,9 +210,11 @@ int main(int argc, char **argv)
     if (!lvvl) for (int jt = (npt > ns ? npt - ns : 0); jt < npt; ++jt) drain(jt % ns, jt);
     tm.mark("records");
     out.w.close();
+    tm.mark("output_closed");
+    if (quick_exit_wanted()) { tm.total(); quick_exit_now(); }
     for (auto p : pbuf) delete p;
     gpu_check(cdfgpu_finalize(), "cdfgpu_finalize");
-    tm.mark("close");
+    tm.mark("teardown");
     tm.total();
     return 0;
 }

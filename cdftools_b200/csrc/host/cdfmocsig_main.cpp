@@ -179,9 +179,11 @@ int main(int argc, char **argv)
     for (int jt = (npt > nslot ? npt - nslot : 0); jt < npt; ++jt) drain(jt % nslot, jt);
     tm.mark("records");
     out.w.close();
+    tm.mark("output_closed");
+    if (quick_exit_wanted()) { tm.total(); quick_exit_now(); }
     for (auto v : {&pv, &pt, &ps, &pe, &p3}) for (auto p : *v) delete p;
     gpu_check(cdfgpu_finalize(), "cdfgpu_finalize");
-    tm.mark("close");
+    tm.mark("teardown");
     tm.total();
     return 0;
 }

@@ -346,6 +346,21 @@ struct OutFile {
     void put(int v, long rec, const float *vals) { nc_check(w.put_f32(varids[v], rec, 0, (uint64_t)nlev * ny, vals), w.err); }
 };
 
+// End of a command-line run, after the output files are closed: the process is about to exit, so the page-locked buffers
+// (cudaFreeHost of several GB costs ~0.1 s per GB) and the CUDA context are left to the operating system.  The device is
+// idle at this point (every record has been fetched).  $CDFGPU_FULL_TEARDOWN=1 frees everything explicitly instead.
+inline bool quick_exit_wanted()
+{
+    const char *e = getenv("CDFGPU_FULL_TEARDOWN");
+    return !(e && atoi(e));
+}
+[[noreturn]] inline void quick_exit_now()
+{
+    fflush(stdout);
+    fflush(stderr);
+    _exit(0);
+}
+
 // pinned record buffers
 struct Pinned {
     float *p = nullptr;

@@ -68,11 +68,36 @@ struct Var {
     }
 };
 
-inline void swap_inplace(void *p, size_t n, size_t es)
+inline void swap_range(void *p, size_t n, size_t es)
 {
     if (es == 2) { uint16_t *q = (uint16_t *)p; for (size_t i = 0; i < n; ++i) q[i] = __builtin_bswap16(q[i]); }
     else if (es == 4) { uint32_t *q = (uint32_t *)p; for (size_t i = 0; i < n; ++i) q[i] = bswap32(q[i]); }
     else if (es == 8) { uint64_t *q = (uint64_t *)p; for (size_t i = 0; i < n; ++i) q[i] = bswap64(q[i]); }
+}
+// threads for the bulk work of the host reader (positional reads of whole records, byte swaps of the mesh fields):
+// $CDFGPU_READ_THREADS, else the hardware's concurrency, at most 16
+inline int io_threads()
+{
+    static int n = 0;
+    if (n == 0) {
+        const char *e = getenv("CDFGPU_READ_THREADS");
+        n = e && atoi(e) > 0 ? atoi(e) : (int)std::thread::hardware_concurrency();
+        n = n < 1 ? 1 : n > 16 ? 16 : n;
+    }
+    return n;
+}
+inline void swap_inplace(void *p, size_t n, size_t es)
+{
+    const int nt = io_threads();
+    if (es == 1) return;
+    if (n < ((size_t)1 << 22) || nt == 1) { swap_range(p, n, es); return; }
+    std::vector<std::thread> th;
+    const size_t chunk = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) {
+        const size_t a = (size_t)t * chunk, b = a + chunk < n ? a + chunk : n;
+        if (a < b) th.emplace_back([=]() { swap_range((char *)p + a * es, b - a, es); });
+    }
+    for (auto &x : th) x.join();
 }
 
 class Reader {
@@ -160,7 +185,7 @@ class Reader {
         if (nb >= ((size_t)64 << 20)) {   // a whole 3-D record: positional reads from several threads (one memcpy stream
                                           // out of the page cache tops out near 3 GB/s, well below PCIe)
             const int fd = fileno(f_);
-            const int nt = 6;
+            const int nt = io_threads();
             const size_t chunk = ((nb + nt - 1) / nt + 4095) & ~(size_t)4095;
             std::vector<std::thread> th;
             std::vector<int> ok(nt, 1);
