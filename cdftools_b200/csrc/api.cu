@@ -164,7 +164,7 @@ static bool pack_masks(int nx, int ny, int nb, const int16_t *ibmask, int pitchw
 // =================================================================================================== cdfmoc
 struct MocPlan {
     bool ready = false;
-    int nx = 0, ny = 0, nz = 0, nb = 0, pitchw = 0, general = 0, chunk = 1, jsplit = 0;
+    int nx = 0, ny = 0, nz = 0, nb = 0, pitchw = 0, general = 0, general_masks = 0, chunk = 1, jsplit = 0;
     float *d_e1v = nullptr, *d_e3m = nullptr, *d_area = nullptr;
     uint32_t *d_maskw = nullptr;
     int16_t *d_ibmask = nullptr;
@@ -288,7 +288,7 @@ static int moc_build_area()
     int flag = 0;
     CDF_CUDA(cudaMemcpyAsync(&flag, moc.d_flag, sizeof(int), cudaMemcpyDeviceToHost, g.s_compute));
     CDF_CUDA(cudaStreamSynchronize(g.s_compute));
-    if (flag) moc.general = 1;
+    moc.general = (moc.general_masks || flag) ? 1 : 0;   // (a later -vvl record with a finite area takes the fast path again)
     return CDFGPU_OK;
 }
 
@@ -584,7 +584,8 @@ static int cdfmoc_gpu_setup_dev(int nx, int ny, int nz, int nb, const float *e1v
     if ((rc = make_ws(moc.ws_ext, ny))) return rc;
     std::vector<uint32_t> words;
     const bool binary = pack_masks(nx, ny, nb, ibmask, moc.pitchw, words);
-    moc.general = binary ? 0 : 1;
+    moc.general_masks = binary ? 0 : 1;
+    moc.general = moc.general_masks;
     CDF_CUDA(cudaMemcpyAsync(moc.d_maskw, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, g.s_compute));
     CDF_CUDA(cudaMemcpyAsync(moc.d_ibmask, ibmask, nxy * nb * sizeof(int16_t), cudaMemcpyHostToDevice, g.s_compute));
     CDF_CUDA(cudaMemcpyAsync(moc.d_e1v, e1v, nxy * sizeof(float), cudaMemcpyHostToDevice, g.s_compute));
