@@ -17,9 +17,9 @@ gridV records, 5 basins.  One STEP = one pass of the hot path over the whole rec
 N > 1: one process per GPU (torchrun).
   time sharding  (cdfmoc workloads, cdfmocsig-ORCA025): every rank owns its own records -> weak scaling
   band sharding  (cdfmocsig-ORCA12-...-bands): every rank owns a latitude band of every record -> strong scaling
-Inside the timed region every rank copies its result slabs to page-locked host memory behind their kernels (--gather
-host, the default: the path has no exchange step and its result is a file); --gather nccl gathers them to rank 0's HBM
-instead (cdftools_b200/shard.py).
+Inside the timed region the per-rank result slabs are gathered to rank 0's HBM over NCCL behind their kernels (--gather
+nccl, the default; cdftools_b200/shard.py); --gather host makes every rank copy its own slabs to page-locked host memory
+instead (no collective at all -- faster at 2 GPUs, host-memory bound at 8); the other mode is measured in a sub-record.
 """
 from __future__ import annotations
 
@@ -787,9 +787,10 @@ def run_ours(args):
         sub("config4", lambda: measure(cx, "cdfmoc-ORCA12-L75-46rec-5basins", steps=3, warmup=3, nrec=6, do_e2e=False), 240)
         sub("config5", lambda: measure(cx, "cdfmocsig-ORCA12-L75-sigma2-158bins-8rec-bands", steps=3, warmup=3, nrec=4,
                                        do_e2e=False), 120)
-        if args.gather != "nccl":   # the headline workload once more with the slabs gathered to rank 0's HBM over NCCL / NVLink
-            sub("gather_nccl", lambda: measure(cx, args.workload, steps=min(args.steps, 5), warmup=3, do_e2e=False, do_smooth=False,
-                                               gather="nccl"), 60)
+        # the headline workload once more with the result slabs leaving the devices the other way
+        other = "host" if args.gather == "nccl" else "nccl"
+        sub("gather_" + other, lambda: measure(cx, args.workload, steps=min(args.steps, 5), warmup=3, do_e2e=False, do_smooth=False,
+                                               gather=other), 60)
     if rank == 0:
         line["sub_records"] = subs
         line["wall_s"] = cx.elapsed()
@@ -819,10 +820,11 @@ def main():
                     help="slabs gathered to rank 0: f32 = converted on the device to what the output file stores (REAL(4), plus "
                          "the derived inp0 for cdfmoc); f64 = the raw fp64 slabs")
     ap.add_argument("--gather-groups", type=int, default=4, help="the slabs of a step are gathered in this many groups")
-    ap.add_argument("--gather", default="host", choices=["host", "nccl", "none"],
-                    help="N>1, where the result slabs go inside the timed region: host = every rank copies its own slabs to "
-                         "page-locked host memory (no collective: the result is a file); nccl = gathered to rank 0's HBM; "
-                         "none = diagnostic, slabs stay on the device (the number is then NOT the job's)")
+    ap.add_argument("--gather", default="nccl", choices=["host", "nccl", "none"],
+                    help="N>1, where the result slabs go inside the timed region: nccl = gathered to rank 0's HBM over NVLink "
+                         "(default); host = every rank copies its own fp64 slabs to page-locked host memory (no collective; at "
+                         "8 GPUs the 160 GB/s of result traffic saturate the host memory system); none = diagnostic, slabs stay "
+                         "on the device (the number is then NOT the job's)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
