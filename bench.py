@@ -237,6 +237,8 @@ class Ctx:
         if self.world > 1:
             # the slab gather is small next to the kernels' traffic: a few NCCL channels keep it off the SMs the persistent
             # kernels occupy (each channel is a resident CTA)
+            if args.spare_sms >= 0:
+                os.environ["CDFGPU_K1_SPARE_SMS"] = str(args.spare_sms)
             if args.nccl_channels > 0:
                 os.environ.setdefault("NCCL_MAX_NCHANNELS", str(args.nccl_channels))
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
@@ -816,6 +818,9 @@ def main():
     ap.add_argument("--no-subrecords", action="store_true", help="headline workload only")
     ap.add_argument("--nccl-channels", type=int, default=0,
                     help="NCCL_MAX_NCHANNELS for the slab gather (unless already set); 0 leaves NCCL's default")
+    ap.add_argument("--spare-sms", type=int, default=-1,
+                    help="N>1 with --gather nccl: SMs the persistent K1 grid leaves to the NCCL kernels ($CDFGPU_K1_SPARE_SMS); "
+                         "-1 = the default for the mode")
     ap.add_argument("--gather-dtype", default="f32", choices=["f32", "f64"],
                     help="slabs gathered to rank 0: f32 = converted on the device to what the output file stores (REAL(4), plus "
                          "the derived inp0 for cdfmoc); f64 = the raw fp64 slabs")

@@ -205,7 +205,11 @@ static int moc_launch_v(const MocParams &p, cudaStream_t st)
         CDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)moc.smem));
         CDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kMocThreads, moc.smem));
         if (occ < 1) return set_error(CDFGPU_ERR_ARG, "cdfmoc: kernel does not fit (nz*nb too large for shared memory)");
-        grid = occ * g.sm_count;
+        // $CDFGPU_K1_SPARE_SMS: leave a few SMs to kernels of other streams (an NCCL slab gather running beside the
+        // persistent grid otherwise takes its SMs from it at the launch boundaries)
+        int spare = 0;
+        if (const char *e = getenv("CDFGPU_K1_SPARE_SMS")) spare = std::max(0, std::min(g.sm_count - 1, atoi(e)));
+        grid = occ * (g.sm_count - spare);
     }
     if (moc.pdl) {   // programmatic dependent launch: consecutive K1 launches of a stream overlap tail and ramp-up
         MocParams q = p;
