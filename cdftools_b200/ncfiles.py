@@ -41,6 +41,9 @@ def write_mesh(m: synth.Mesh, outdir, with_basins=True, version=2, zgr="v3.6"):
     for name, arr in (("e1v", m.e1v), ("e1u", m.e1u), ("e2v", e2v), ("e2u", e2u), ("gphiv", m.gphiv), ("glamv", m.glamv)):
         v = f.createVariable(name, "f", ("t", "y", "x"))
         v[0] = arr
+    for name, arr in (("nav_lon", m.glamv), ("nav_lat", m.gphiv)):   # as every NEMO mesh file carries them
+        v = f.createVariable(name, "f", ("y", "x"))
+        v[:] = arr
     f.close()
     f = _new(out / "mesh_zgr.nc", {"x": nx, "y": ny, "z": nz, "t": None, **({"x_a": 1, "y_a": 1} if zgr == "v2.0" else {})}, version)
     e3u = (m.e3v_0 * np.float32(1.01)).astype(np.float32)
@@ -109,6 +112,8 @@ def write_gridt(m: synth.Mesh, path, nrec, spval=0.0, version=2, first=0):
     nz, ny, nx = m.e3v_0.shape
     f = _new(path, {"x": nx, "y": ny, "deptht": nz, "time_counter": None}, version)
     tc = f.createVariable("time_counter", "d", ("time_counter",))
+    dep = f.createVariable("deptht", "f", ("deptht",))
+    dep[:] = m.gdept_1d.astype(np.float32)
     t = f.createVariable("votemper", "f", ("time_counter", "deptht", "y", "x"))
     s = f.createVariable("vosaline", "f", ("time_counter", "deptht", "y", "x"))
     t.missing_value = np.float32(spval)

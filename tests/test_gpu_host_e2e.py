@@ -459,6 +459,98 @@ def test_cdfsigtrp_cli_full_step_and_errors(tools, oracle_mod, tmp_path):
     f = netcdf_file(str(tmp_path / "line_trpsig.nc"), "r", mmap=False)
     assert np.array_equal(f.variables["sigtrp"][0, :, 0, 0], (o["dtrpbin"] / 1.e6).astype(np.float32))
     f.close()
-    for bad, code in ((base[:-4], 99), (base + ["-xtra"], 99), (base + ["-bogus"], 99), (["-t", "nofile.nc"] + base[2:], 99)):
+    for bad, code in ((base[:-4], 99), (base + ["-vvl"], 99), (base + ["-bogus"], 99), (["-t", "nofile.nc"] + base[2:], 99)):
         r = subprocess.run([tools["cdfsigtrp_gpu"]] + bad, capture_output=True, text=True, cwd=tmp_path, timeout=120)
         assert r.returncode == code, (bad, r.stdout)
+
+
+def test_cdfsigtrp_cli_xtra_and_print(tools, oracle_mod, tmp_path):
+    """-xtra: <section>_secdep.nc / _secsig.nc (cdf_writ, src/cdfsigtrp.f90:750-900) and -print: the tables of print_out
+    (:902-963), from the arrays the library returns -- bit-identical to the oracle's after the REAL(4) conversion."""
+    m = synth.make_mesh("SMALL")
+    ncfiles.write_mesh(m, tmp_path)
+    u = ncfiles.write_gridu(m, tmp_path / "gridU.nc", 1)[0]
+    v = ncfiles.write_gridv(m, tmp_path / "gridV.nc", 1)[0]
+    t, s = ncfiles.write_gridt(m, tmp_path / "SYN_gridT.nc", 1)[0]
+    secs = {"zon": (20, 60, 17, 17), "mer": (60, 60, 4, 33)}
+    (tmp_path / "dens_section.dat").write_text("zon z Zlong\n20 60 17 17\nmer\n60 60 4 33\nEOF\n")
+    nbins = 12
+    out = _run(tools["cdfsigtrp_gpu"], ["-t", "SYN_gridT.nc", "-u", "gridU.nc", "-v", "gridV.nc", "-smin", "23", "-smax", "28.4", "-nbins",
+                                        str(nbins), "-xtra", "-print"], tmp_path)
+    lines = out.splitlines()
+    for name, sec in secs.items():
+        p, o = _sigtrp_expected(oracle_mod, m, u, v, t, s, sec, 23.0, 28.4, nbins)
+        nk, npts = p["nk"], p["zu"].shape[1]
+        sfx = "_z" if name == "zon" else ""
+        f = netcdf_file(str(tmp_path / (name + "_secdep.nc")), "r", mmap=False)
+        assert f.variables["temperature" + sfx].shape == (1, nk, 1, npts) and f.variables["density" + sfx].units == b"kg/m3 -1000"
+        assert np.array_equal(f.variables["temperature" + sfx][0, :, 0, :], p["zt"][:nk])
+        assert np.array_equal(f.variables["salinity" + sfx][0, :, 0, :], p["zs"][:nk])
+        assert np.array_equal(f.variables["density" + sfx][0, :, 0, :], o["dsig"][1:].astype(np.float32))
+        assert np.array_equal(f.variables["velocity" + sfx][0, :, 0, :], p["zu"][:nk])
+        assert np.allclose(f.variables["deptht"][:], m.gdept_1d[:nk]) and f.variables["velocity" + sfx].axis == b"XZT"
+        if name == "zon":
+            assert f.variables["temperature_z"].long_name == b"Zlong_Potential_temperature"
+        f.close()
+        f = netcdf_file(str(tmp_path / (name + "_secsig.nc")), "r", mmap=False)
+        assert f.variables["isodep" + sfx].shape == (1, nbins, 1, npts) and f.variables["sumtrp" + sfx].units == b"SV"
+        assert np.array_equal(f.variables["isodep" + sfx][0, :nbins - 1, 0, :], o["dhiso"][:nbins - 1].astype(np.float32))
+        assert np.array_equal(f.variables["bintrp" + sfx][0, :, 0, :], (o["dwtrpbin"] / 1.e6).astype(np.float32))
+        assert np.array_equal(f.variables["sumtrp" + sfx][0, :, 0, :], (o["dwtrp"][:nbins] / 1.e6).astype(np.float32))
+        assert np.array_equal(f.variables["levels"][:], o["dsigma_lev"][:nbins].astype(np.float32))
+        f.close()
+    # the tables of the first (zonal) section: (i7, npts f8.3) rows of T, then (f7.3, npts f8.0) rows of the isopycnal depths
+    p, o = _sigtrp_expected(oracle_mod, m, u, v, t, s, secs["zon"], 23.0, 28.4, nbins)
+    npts = p["zu"].shape[1]
+    i0 = lines.index("  T (deg C)")
+    row = lines[i0 + 1]
+    assert len(row) == 7 + 8 * npts and int(row[:7]) == 1
+    assert np.allclose([float(row[7 + 8 * i: 15 + 8 * i]) for i in range(npts)], p["zt"][0], atol=5.1e-4)
+    i1 = lines.index("  DEP ISO ( m )")
+    row = lines[i1 + 3]
+    assert float(row[:7]) == pytest.approx(o["dsigma_lev"][2], abs=5.1e-4) and row[7:15].endswith(".")
+    assert np.allclose([float(row[7 + 8 * i: 15 + 8 * i]) for i in range(npts)], o["dhiso"][2], atol=0.51)
+    i2 = lines.index("  TRP bins (SV)")
+    assert float(lines[i2 + 2]) == pytest.approx(o["dtrpbin"][0] / 1.e6, abs=5.1e-4)     # the total of the bin on a record of its own
+
+
+def test_cdfsigtrp_cli_broken_line(tools, oracle_mod, tmp_path):
+    """-brk: a broken-line file (as cdf_xtrac_brokenline writes it) is one pseudo-zonal section holding its own metrics,
+    local depths and mask (src/cdfsigtrp.f90:465-495, :608); the section is named after the file."""
+    from cdftools_b200.ncfiles import _new
+    sec = synth.make_section(48, 31, seed=9)
+    p = oracle_mod.sigtrp_prepare(sec["gdept"][0], sec["e3w_a"], sec["e3w_b"], sec["zu"], 0.0, sec["zs_a"], sec["zs_b"], 0.0, sec["zt_a"],
+                                  sec["zt_b"])
+    npk, npts = p["zu"].shape
+    nxf = npts + 1                                  # the tool uses columns 1 .. npiglo-1
+    depw = (np.repeat(sec["gdepw"][:, None], npts, axis=1) * np.linspace(0.95, 1.05, npts, dtype=np.float32)[None]).astype(np.float32)
+    mask = p["zmask"].copy()
+    mask[-1, ::5] = 9999.0                          # the fill value of the broken-line masks counts as land (:486)
+    f = _new(tmp_path / "SYN_y2026_brk_denmark.nc", {"x": nxf, "y": 1, "depthv": npk, "time_counter": None})
+    tc = f.createVariable("time_counter", "d", ("time_counter",)); tc[0] = 777.0
+
+    def put(name, arr, dims=("time_counter", "depthv", "y", "x")):
+        var = f.createVariable(name, "f", dims)
+        full = np.zeros(arr.shape[:-1] + (nxf,), np.float32)
+        full[..., :npts] = arr
+        if len(dims) == 4:
+            var[0, :, 0, :] = full
+        else:
+            var[0, :] = full
+        return var
+
+    put("e1v", sec["eu"][None], ("y", "x")); put("nav_lon", np.linspace(-30, -20, npts, dtype=np.float32)[None], ("y", "x"))
+    put("e3v", sec["de3"]); put("depu3d", p["ddepu"][1:].astype(np.float32)); put("depw3d", depw)
+    put("vomecrty", p["zu"]); put("votemper", p["zt"]); put("vosaline", p["zs"]); put("vmask", mask)
+    f.close()
+    _run(tools["cdfsigtrp_gpu"], ["-brk", "SYN_y2026_brk_denmark.nc", "-smin", "24", "-smax", "28.2", "-nbins", "14"], tmp_path)
+    zmask = np.where(mask == 9999.0, 0.0, mask).astype(np.float32)
+    nk = next((k + 1 for k in range(npk) if zmask[k].sum() == 0), npk)
+    ddepu = np.concatenate([np.zeros((1, npts)), p["ddepu"][1:].astype(np.float32).astype(np.float64)])
+    o = oracle_mod.sigtrp_section(sec["eu"], sec["de3"], ddepu, sec["gdepw"], p["zu"], p["zt"], p["zs"], zmask, nk, 24.0, 28.2, 14,
+                                  ddepw_brk=depw)
+    f = netcdf_file(str(tmp_path / "denmark_trpsig.nc"), "r", mmap=False)
+    got = f.variables["sigtrp_denmark"][0, :, 0, 0]
+    assert f.variables["sigtrp_denmark"].long_name == b"denmark_transport in sigma class" and f.variables["time_counter"][0] == 777.0
+    assert np.any(got != 0) and np.array_equal(got, (o["dtrpbin"] / 1.e6).astype(np.float32))
+    f.close()
