@@ -364,14 +364,24 @@ def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=T
     diff64 = torch.empty((gmax,) + out_shape[:-1], dtype=torch.float64, device="cuda") if (do_gather and g32 and nvar > nb) else None
     gathered = [None, None]   # per output buffer: the event that marks its last gather as complete
 
+    # cdfmoc: the records of a group go to the device as ONE persistent launch (cdfmoc_gpu_compute_device_batch: the work
+    # units run over (record, row, levels), so launch overhead, ramp-up and tail are paid once per group) unless
+    # --k1-launch record asks for one launch per record (what the submit / fetch record pipeline issues)
+    k1_batch = (not sig) and args.k1_launch == "batch"
+    zlists = [[recs[r % n_res][0] for r in range(gb[g], gb[g + 1])] for g in range(ngroups)]
+    olists = [[[outs[b][r] for r in range(gb[g], gb[g + 1])] for g in range(ngroups)] for b in range(2)]
+
     def kernel_step(i):
         o = outs[i & 1]
         if gathered[i & 1] is not None:
             st.wait_event(gathered[i & 1])   # this buffer's slabs of two steps ago must have left before it is overwritten
         for g in range(ngroups):
             with torch.cuda.stream(st):
-                for r in range(gb[g], gb[g + 1]):
-                    launch(recs[r % n_res], o[r])
+                if k1_batch:
+                    lib.cdfmoc_compute_device_batch(zlists[g], olists[i & 1][g], st)
+                else:
+                    for r in range(gb[g], gb[g + 1]):
+                        launch(recs[r % n_res], o[r])
             if do_host:
                 ev = torch.cuda.Event()
                 ev.record(st)
@@ -426,10 +436,13 @@ def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=T
 
     # ---- roofline of the workload's kernel: algorithmic bytes per launch / average launch time (same events)
     hbm_peak = cx.hbm_peak
-    ms_launch = ms_total / (steps * nrec)
-    achieved = bytes_launch / (ms_launch * 1e-3) / 1e9
+    ms_record = ms_total / (steps * nrec)
+    achieved = bytes_launch / (ms_record * 1e-3) / 1e9
+    rpl = nrec / ngroups if k1_batch else 1.0          # records per launch
+    ms_launch = ms_record * rpl
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "kernel": kname, "bytes_per_launch": bytes_launch, "ms_per_launch": ms_launch,
+                "traffic": None, "kernel": kname, "bytes_per_launch": int(bytes_launch * rpl), "ms_per_launch": ms_launch,
+                "records_per_launch": rpl, "bytes_per_record": bytes_launch, "ms_per_record": ms_record,
                 "peak_source": cx.peak_src, "frac_of_8TBps_spec": achieved / 8000.0,
                 "note": "per-GPU figure; at N>1 the launch time includes the overlapped copy of the result slabs (--gather)",
                 "peak_kind": "measured device-to-device COPY bandwidth (read + write); a read-only streaming kernel can "
@@ -438,7 +451,7 @@ def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=T
     if tp.exists() and spec["grid"] == "ORCA025" and not band:
         try:
             tj = json.loads(tp.read_text())
-            roofline["traffic"] = tj["dram_bytes_per_launch"]
+            roofline["traffic"] = tj["dram_bytes_per_launch"] * rpl   # (the capture is one record)
             roofline["traffic_source"] = "committed ncu capture of this kernel on this grid (%s), not a counter of this run" % tp.name
             if sig and "warp_inst_per_launch" in tj:
                 roofline["warp_inst_per_launch"] = tj["warp_inst_per_launch"]
@@ -551,9 +564,8 @@ def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=T
                                  "note": "same launches with ts_noise = 0 (T/S as smooth as the stratification)"}
     filt = lib.cdfmocsig_filter_info() if sig else None
 
-    # ---- cdfmoc only: the same step as ONE batched launch (cdfmoc_gpu_compute_device_batch): work units run over (record,
-    # row, levels), so launch overhead, ramp-up and tail are paid once per step.  Reported beside the headline, which stays
-    # one launch per record (what the record pipeline issues).
+    # ---- cdfmoc only: the same records with the OTHER launch mode (no slab gather): one launch per record when the
+    # headline is batched, one batched launch per step otherwise
     if not sig:
         o = outs[0]
         zl = [recs[r % n_res][0] for r in range(nrec)]
@@ -564,15 +576,21 @@ def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=T
             with torch.cuda.stream(st):
                 e0.record(st)
                 for _ in range(3):
-                    lib.cdfmoc_compute_device_batch(zl, ol, st)
+                    if k1_batch:
+                        for r in range(nrec):
+                            lib.cdfmoc_compute_device(zl[r], ol[r], st)
+                    else:
+                        lib.cdfmoc_compute_device_batch(zl, ol, st)
                 e1.record(st)
             st.synchronize()
         ms_b = cx.max_over_ranks(e0.elapsed_time(e1)) / (3 * nrec)
         ach_b = bytes_launch / (ms_b * 1e-3) / 1e9
         same = bool(torch.equal(o[0], outs[1][0])) if steps > 1 else None
-        roofline["batched"] = {"ms_per_record": ms_b, "achieved": ach_b, "frac": ach_b / hbm_peak,
-                               "records_per_launch": nrec, "equals_single_launches": same,
-                               "note": "cdfmoc_gpu_compute_device_batch: one persistent launch per step over all records"}
+        roofline["per_record_launches" if k1_batch else "batched"] = {
+            "ms_per_record": ms_b, "achieved": ach_b, "frac": ach_b / hbm_peak, "records_per_launch": 1 if k1_batch else nrec,
+            "equals_headline_result": same,
+            "note": ("cdfmoc_gpu_compute_device: one launch per record (programmatic dependent launch), what cdfmoc_gpu_submit issues"
+                     if k1_batch else "cdfmoc_gpu_compute_device_batch: one persistent launch per step over all records")}
 
     cb = None
     if do_cpu and rank == 0 and world == 1:
@@ -594,6 +612,9 @@ def measure(cx: Ctx, workload: str, steps: int, warmup: int, nrec=None, do_e2e=T
                                  "their kernels, inside the timed region (the result is a file: no rank needs the others' slabs "
                                  "in HBM)" % ngroups) if do_host else
                                 ("SKIPPED (--gather none diagnostic)" if world > 1 else None),
+                      "launches": ("one persistent launch per %s (%d records): cdfmoc_gpu_compute_device_batch"
+                                   % ("step" if ngroups == 1 else "gather group", int(round(rpl)))) if k1_batch else
+                                  "one launch per record, programmatic dependent launch between them",
                       "wet_fraction": m.wet_fraction}}
     if e2e:
         rec["e2e"] = e2e
@@ -818,6 +839,9 @@ def main():
     ap.add_argument("--no-subrecords", action="store_true", help="headline workload only")
     ap.add_argument("--nccl-channels", type=int, default=0,
                     help="NCCL_MAX_NCHANNELS for the slab gather (unless already set); 0 leaves NCCL's default")
+    ap.add_argument("--k1-launch", default="batch", choices=["batch", "record"],
+                    help="cdfmoc workloads: batch = the records of a step (of a gather group at N>1) in one persistent launch "
+                         "(cdfmoc_gpu_compute_device_batch); record = one launch per record")
     ap.add_argument("--spare-sms", type=int, default=-1,
                     help="N>1 with --gather nccl: SMs the persistent K1 grid leaves to the NCCL kernels ($CDFGPU_K1_SPARE_SMS); "
                          "-1 = the default for the mode")
