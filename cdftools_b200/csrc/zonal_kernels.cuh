@@ -7,6 +7,8 @@
 // never contracted: the library is built with -fmad=false); only the order of the fp64 additions along i differs from
 // the reference's sequential loop.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace cdfgpu {
@@ -37,12 +39,39 @@ __device__ __forceinline__ double warp_min(double v)
 template <int NB, bool MEAN, bool BITS>
 struct ZonalAcc {
     double acc[NB], area[MEAN ? NB : 1], dmax[MEAN ? NB : 1], dmin[MEAN ? NB : 1];
+    float zf;   // fast path: NaN as soon as a product of the lane was not finite
     __device__ __forceinline__ void init()
     {
+        zf = 0.0f;
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             acc[b] = 0.0;
             if (MEAN) { area[b] = 0.0; dmax[b] = -INFINITY; dmin[b] = INFINITY; }
+        }
+    }
+    // Fast form of a cell for 0 / 1 basin masks and finite data (no zonal max / min): the reference adds d*dtmp(mask = 1) or
+    // d*dtmp(mask = 0) = +-0 to every basin's sum; fma(t1, m, acc) with m = 1.0 / 0.0 taken from the mask bit gives
+    // acc + t1 (one rounding, t1*1 is exact) and acc + (+-0) = acc -- one integer multiply and one DFMA per basin instead
+    // of a bit test, two FSELs and a DADD.  With non-finite data the mask-0 term is NaN in the reference (0*Inf) but can be
+    // +-0 here and vice versa: zf turns NaN then and the warp redoes the row with cell().
+    __device__ __forceinline__ void cell_fast(float v, float mv, double d, unsigned bits)
+    {
+        double t1, a1 = 0.0;
+        if (!MEAN) {
+            const float p1 = __fmul_rn(mv, v);   // fl32(fl32(1*mv)*v)
+            zf = __fmaf_rn(p1, 0.0f, zf);
+            t1 = __dmul_rn(d, (double)p1);
+        } else {
+            zf = __fmaf_rn(mv, 0.0f, __fmaf_rn(v, 0.0f, zf));
+            const double dmv = (double)mv;
+            t1 = __dmul_rn(d, __dmul_rn(dmv, (double)v));
+            a1 = __dmul_rn(d, dmv);
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const double m = __hiloint2double((int)((bits & (1u << b)) * (0x3FF00000u >> b)), 0);   // 1.0 or 0.0
+            acc[b] = __fma_rn(t1, m, acc[b]);
+            if (MEAN) area[b] = __fma_rn(a1, m, area[b]);
         }
     }
     // one cell: v = zv, mv = zmaskvar, d = dl_surf, bits = packed masks (BITS) or pz = the cell in plane 0 (!BITS)
@@ -114,26 +143,40 @@ __global__ void __launch_bounds__(256) zonal_rows_kernel(const float *__restrict
         const float *pz = zmask + (size_t)j * nx;
         const uint8_t *pb = zbits + (size_t)j * nx;
         ZonalAcc<NB, MEAN, BITS> A;
-        A.init();
         const int head = min((int)((4 - (e0 & 3)) & 3), nx);   // scalar cells in front of the first 16-byte boundary
         const int nvec = (nx - head) >> 2;
         const int tail0 = head + 4 * nvec;
-        {   // head and tail cells (at most 3 + 3), one per lane
-            int i = -1;
-            if (lane < head) i = lane;
-            else if (lane - head < nx - tail0) i = tail0 + lane - head;
-            if (i >= 0) A.cell(__ldg(pv + i), __ldg(pm + i), __ldg(pd + i), BITS ? (unsigned)__ldg(pb + i) : 0u, pz + i, nxy, lmax);
-        }
+        auto sweep = [&](auto fast_tag) {
+            constexpr bool FAST = decltype(fast_tag)::value;
+            A.init();
+            {   // head and tail cells (at most 3 + 3), one per lane
+                int i = -1;
+                if (lane < head) i = lane;
+                else if (lane - head < nx - tail0) i = tail0 + lane - head;
+                if (i >= 0) {
+                    if (FAST) A.cell_fast(__ldg(pv + i), __ldg(pm + i), __ldg(pd + i), (unsigned)__ldg(pb + i));
+                    else A.cell(__ldg(pv + i), __ldg(pm + i), __ldg(pd + i), BITS ? (unsigned)__ldg(pb + i) : 0u, pz + i, nxy, lmax);
+                }
+            }
 #pragma unroll 2
-        for (int vi = lane; vi < nvec; vi += 32) {
-            const int i = head + 4 * vi;
-            const float4 v = ld_stream_f4(reinterpret_cast<const float4 *>(pv + i), pol);
-            const float4 m = __ldg(reinterpret_cast<const float4 *>(pm + i));
-            const float vv[4] = {v.x, v.y, v.z, v.w}, mm[4] = {m.x, m.y, m.z, m.w};
+            for (int vi = lane; vi < nvec; vi += 32) {
+                const int i = head + 4 * vi;
+                const float4 v = ld_stream_f4(reinterpret_cast<const float4 *>(pv + i), pol);
+                const float4 m = __ldg(reinterpret_cast<const float4 *>(pm + i));
+                const float vv[4] = {v.x, v.y, v.z, v.w}, mm[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                A.cell(vv[c], mm[c], __ldg(pd + i + c), BITS ? (unsigned)__ldg(pb + i + c) : 0u, pz + i + c, nxy, lmax);
+                for (int c = 0; c < 4; ++c) {
+                    if (FAST) A.cell_fast(vv[c], mm[c], __ldg(pd + i + c), (unsigned)__ldg(pb + i + c));
+                    else A.cell(vv[c], mm[c], __ldg(pd + i + c), BITS ? (unsigned)__ldg(pb + i + c) : 0u, pz + i + c, nxy, lmax);
+                }
+            }
+        };
+        bool fast = BITS && !lmax;   // warp-uniform
+        if (fast) {
+            sweep(std::true_type{});
+            if (__any_sync(kFull, A.zf != A.zf)) fast = false;   // a non-finite product somewhere in the row: the literal chain
         }
+        if (!fast) sweep(std::false_type{});
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             const double s = warp_sum(A.acc[b]);
