@@ -8,7 +8,7 @@ import pytest
 from scipy.io import netcdf_file
 
 from cdftools_b200 import build, ncfiles, synth
-from util import assert_psi_close, case_inputs
+from util import assert_psi_close, case_inputs, sigtrp_expected as _sigtrp_expected
 
 pytestmark = pytest.mark.gpu
 
@@ -363,33 +363,6 @@ def test_cdfmoc_cli_nam_cdf_names_and_nc4(tools, oracle_mod, tmp_path):
     (tmp_path / "nam_cdf_names").unlink()
     r = subprocess.run([tools["cdfmoc_gpu"], "-v", "gridV.nc"], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 99 and "mesh_hgr.nc is missing" in r.stdout
-
-
-def _sigtrp_expected(oracle_mod, m, u, v, t, s, sec, smin, smax, nbins, spval=0.0, **kw):
-    """What cdfsigtrp computes for one section from the arrays the files hold (src/cdfsigtrp.f90:404-627)."""
-    imin, imax, jmin, jmax = sec
-    e3w_1d, e3w = ncfiles.e3w_fields(m)
-    e2u = (m.e1u * np.float32(0.9)).astype(np.float32)
-    e3u = (m.e3v_0 * np.float32(1.01)).astype(np.float32)
-    if imin == imax:   # meridional: rows jmin+1 .. jmax at column imin, T / S also at imin+1
-        rows, i0 = slice(jmin, jmax), imin - 1
-        cut = lambda a, i: np.ascontiguousarray(a[:, rows, i])
-        eu, de3 = e2u[rows, i0].copy(), cut(e3u, i0)
-        raw = dict(e3w_a=cut(e3w, i0), e3w_b=cut(e3w, i0 + 1), zu=cut(u, i0), zs_a=cut(s, i0), zs_b=cut(s, i0 + 1), zt_a=cut(t, i0),
-                   zt_b=cut(t, i0 + 1))
-        merid = True
-    else:              # zonal: columns imin+1 .. imax at row jmin, T / S also at jmin+1; e1v starts at imin (as the reference reads it)
-        cols, j0 = slice(imin, imax), jmin - 1
-        cut = lambda a, j: np.ascontiguousarray(a[:, j, cols])
-        eu, de3 = m.e1v[j0, imin - 1:imax - 1].copy(), cut(m.e3v_0, j0)
-        raw = dict(e3w_a=cut(e3w, j0), e3w_b=cut(e3w, j0 + 1), zu=cut(v, j0), zs_a=cut(s, j0), zs_b=cut(s, j0 + 1), zt_a=cut(t, j0),
-                   zt_b=cut(t, j0 + 1))
-        merid = False
-    p = oracle_mod.sigtrp_prepare(m.gdept_1d[0], raw["e3w_a"], raw["e3w_b"], raw["zu"], spval, raw["zs_a"], raw["zs_b"], spval, raw["zt_a"],
-                                  raw["zt_b"], merid=merid)
-    o = oracle_mod.sigtrp_section(eu, de3, p["ddepu"], m.gdepw_1d.astype(np.float32), p["zu"], p["zt"], p["zs"], p["zmask"], p["nk"], smin,
-                                  smax, nbins, **kw)
-    return p, o
 
 
 @pytest.mark.parametrize("args,kw,lims", [([], {}, (23.0, 28.5, 22)), (["-refdep", "2000"], dict(refdep=2000.0), (31.0, 37.5, 26)),

@@ -30,7 +30,7 @@ BIN = ROOT / "baseline" / "_ref" / "bin"
 def _cases():
     have = sorted(p.parent.name for p in REF.glob("*/case.json"))
     if not have and (BIN / "cdfmoc").exists() and (BIN / "cdfmocsig").exists():
-        have = sorted(rc.CASES)
+        have = sorted(c for c, v in rc.CASES.items() if (BIN / v[3]).exists())
     return have
 
 
@@ -57,7 +57,7 @@ def _reference_file(case, tmp_path):
 
 def _variables(path):
     f = netcdf_file(str(path), "r", mmap=False)
-    out = {k: np.array(v[:]) for k, v in f.variables.items() if k.startswith(("zomsf", "zoiso"))}
+    out = {k: np.array(v[:]) for k, v in f.variables.items() if k.startswith(("zomsf", "zoiso", "sigtrp", "sigma_class"))}
     f.close()
     return out
 
@@ -106,6 +106,22 @@ def test_oracle_matches_the_fortran_reference(oracle_mod, tmp_path, case):
             out = oracle_mod.cdfmocsig_output(psi)
             for iv, n in enumerate(["zomsfglo", "zomsfatl", "zomsfinp", "zomsfind", "zomsfpac"][: psi.shape[2]]):
                 _close(out[iv], ref[n][r, :, :, 0], f"{case} rec {r} {n}")
+        elif tool == "cdfsigtrp":
+            from util import sigtrp_expected
+            uf = netcdf_file(str(d / "gridU.nc"), "r", mmap=False)
+            u = np.array(uf.variables["vozocrtx"][r], np.float32)
+            uf.close()
+            t = np.array(tf.variables["votemper"][r], np.float32)
+            s = np.array(tf.variables["vosaline"][r], np.float32)
+            name = rc.CASES[case][5].replace("_trpsig.nc", "")
+            kw = dict(refdep=float(argv[argv.index("-refdep") + 1])) if "-refdep" in argv else {}
+            smin, smax, nbins = float(argv[argv.index("-smin") + 1]), float(argv[argv.index("-smax") + 1]), int(argv[argv.index("-nbins") + 1])
+            vfull = np.array(vf.variables["vomecrty"][r], np.float32)
+            # spval: the V file carries 1e20 on land, the U file 0 (no missing-value attribute)
+            _, o = sigtrp_expected(oracle_mod, m, u, np.where(vfull == np.float32(1.0e20), np.float32(0), vfull), t, s,
+                                   rc.SIGTRP_SECTIONS[name], smin, smax, nbins, spval=1.0e20, **kw)
+            _close((o["dtrpbin"] / 1.e6).astype(np.float32), ref["sigtrp"][0, :, 0, 0], f"{case} sigtrp")
+            assert np.array_equal(ref["sigma_class"][0, :, 0, 0], o["dsigma_lev"][:nbins].astype(np.float32))
     vf.close()
     tf.close()
 
@@ -118,9 +134,14 @@ def test_gpu_twin_matches_the_fortran_reference(tmp_path, case):
     tools = build.build_host()
     ref_path, d = _reference_file(case, tmp_path)
     tool, argv, fout = rc.CASES[case][3:6]
-    r = subprocess.run([str(tools[tool + "_gpu"])] + argv + ["-o", "gpu_" + fout], cwd=d, capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout + r.stderr
-    ref, got = _variables(ref_path), _variables(d / ("gpu_" + fout))
+    if tool == "cdfsigtrp":   # no -o: the output files are named after the sections
+        r = subprocess.run([str(tools[tool + "_gpu"])] + argv, cwd=d, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        ref, got = _variables(ref_path), _variables(d / fout)
+    else:
+        r = subprocess.run([str(tools[tool + "_gpu"])] + argv + ["-o", "gpu_" + fout], cwd=d, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        ref, got = _variables(ref_path), _variables(d / ("gpu_" + fout))
     assert set(ref) == set(got), (sorted(ref), sorted(got))
     for n in sorted(ref):
         _close(got[n], ref[n], f"{case} {n}")
