@@ -77,42 +77,6 @@ struct Field {   // one (t,z,y,x) variable of an open file
     }
 };
 
-// Fortran E16.7: 0.ddddddd scaled, exponent of two digits
-static std::string e16_7(double x)
-{
-    char b[64];
-    if (x == 0.0 || !std::isfinite(x)) {
-        snprintf(b, sizeof b, "%16s", !std::isfinite(x) ? (std::isnan(x) ? "NaN" : (x > 0 ? "Infinity" : "-Infinity")) : "0.0000000E+00");
-        return b;
-    }
-    snprintf(b, sizeof b, "%.6E", fabs(x));   // d.ddddddE+xx, correctly rounded to 7 significant digits
-    const int ex = atoi(strchr(b, 'E') + 1) + 1;
-    std::string dig;
-    dig += b[0];
-    dig.append(b + 2, 6);
-    char o[64];
-    snprintf(o, sizeof o, "%s0.%sE%c%02d", x < 0 ? "-" : "", dig.c_str(), ex < 0 ? '-' : '+', abs(ex));
-    snprintf(b, sizeof b, "%16s", o);
-    return b;
-}
-
-// Fortran Fw.d edit descriptor: right-justified, asterisks when the value does not fit; d = 0 keeps the decimal point
-static std::string ffmt(double x, int w, int d)
-{
-    char b[64];
-    if (std::isnan(x)) snprintf(b, sizeof b, "%*s", w, "NaN");
-    else if (std::isinf(x)) snprintf(b, sizeof b, "%*s", w, x > 0 ? "Infinity" : "-Infinity");
-    else if (d == 0) snprintf(b, sizeof b, "%*.0f.", w - 1, x);
-    else snprintf(b, sizeof b, "%*.*f", w, d, x);
-    std::string r = b;
-    if ((int)r.size() > w) {   // gfortran drops the optional leading zero before giving up
-        const size_t z = r.find("0.");
-        if (z != std::string::npos && (z == 0 || r[z - 1] == '-' || r[z - 1] == ' ') && (int)r.size() == w + 1) r.erase(z, 1);
-    }
-    if ((int)r.size() > w) r.assign(w, '*');
-    return r;
-}
-
 static void file_example()
 {
     printf("\n   EXAMPLE of dens_section.dat file\n   --------------------------------\n"
@@ -370,8 +334,8 @@ int main(int argc, char **argv)
             auto table = [&](const char *title, int w0, int d0, int nrow, int d, auto label, auto value) {
                 printf(" %s\n", title);
                 for (int r = 0; r < nrow; ++r) {
-                    if (d0 < 0) printf("%*d", w0, (int)label(r)); else printf("%s", ffmt(label(r), w0, d0).c_str());
-                    for (int i = 0; i < npts; ++i) printf("%s", ffmt(value(i, r), 8, d).c_str());
+                    if (d0 < 0) printf("%*d", w0, (int)label(r)); else printf("%s", fortran_f(label(r), w0, d0).c_str());
+                    for (int i = 0; i < npts; ++i) printf("%s", fortran_f(value(i, r), 8, d).c_str());
                     printf("\n");
                 }
             };
@@ -387,9 +351,9 @@ int main(int argc, char **argv)
             table(" TRP SURF -->  ISO (SV)", 7, 3, nbins + 1, 3, cls, [&](int i, int l) { return dwtrp[(size_t)l * npts + i] / 1.e6; });
             printf("  TRP bins (SV)\n");
             for (int b = 0; b < nbins; ++b) {   // one value more than the format holds: it goes to a record of its own (format reversion)
-                printf("%s", ffmt(dsigma_lev[b], 7, 3).c_str());
-                for (int i = 0; i < npts; ++i) printf("%s", ffmt(dwtrpbin[(size_t)b * npts + i] / 1.e6, 8, 3).c_str());
-                printf("\n%s\n", ffmt(trp[b] / 1.e6, 7, 3).c_str());
+                printf("%s", fortran_f(dsigma_lev[b], 7, 3).c_str());
+                for (int i = 0; i < npts; ++i) printf("%s", fortran_f(dwtrpbin[(size_t)b * npts + i] / 1.e6, 8, 3).c_str());
+                printf("\n%s\n", fortran_f(trp[b] / 1.e6, 7, 3).c_str());
             }
         }
         if (lxtra) {   // cdf_writ (:750-900): two (along section, depth | sigma) files
@@ -469,7 +433,7 @@ int main(int argc, char **argv)
         fprintf(f, "\n");
         for (int b = 0; b < nbins; ++b) {
             fprintf(f, "%9.4f", dsigma_lev[b]);
-            for (size_t jsec = 0; jsec < sec.size(); ++jsec) fprintf(f, "%s", e16_7(dtrpbin[jsec * nbins + b]).c_str());
+            for (size_t jsec = 0; jsec < sec.size(); ++jsec) fprintf(f, "%s", fortran_e16_7(dtrpbin[jsec * nbins + b]).c_str());
             fprintf(f, "\n");
         }
         fclose(f);

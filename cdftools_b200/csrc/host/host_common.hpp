@@ -5,6 +5,7 @@
 #pragma once
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include <sys/stat.h>
 
 #include <ctype.h>
@@ -345,6 +346,43 @@ struct OutFile {
     // one record of one variable: vals[lev][j]
     void put(int v, long rec, const float *vals) { nc_check(w.put_f32(varids[v], rec, 0, (uint64_t)nlev * ny, vals), w.err); }
 };
+
+// ---- Fortran edit descriptors, as gfortran prints them (the ASCII outputs of the tools) --------------------------------
+// Fortran E16.7: 0.ddddddd scaled, exponent of two digits
+inline std::string fortran_e16_7(double x)
+{
+    char b[64];
+    if (x == 0.0 || !std::isfinite(x)) {
+        snprintf(b, sizeof b, "%16s", !std::isfinite(x) ? (std::isnan(x) ? "NaN" : (x > 0 ? "Infinity" : "-Infinity")) : "0.0000000E+00");
+        return b;
+    }
+    snprintf(b, sizeof b, "%.6E", fabs(x));   // d.ddddddE+xx, correctly rounded to 7 significant digits
+    const int ex = atoi(strchr(b, 'E') + 1) + 1;
+    std::string dig;
+    dig += b[0];
+    dig.append(b + 2, 6);
+    char o[64];
+    snprintf(o, sizeof o, "%s0.%sE%c%02d", x < 0 ? "-" : "", dig.c_str(), ex < 0 ? '-' : '+', abs(ex));
+    snprintf(b, sizeof b, "%16s", o);
+    return b;
+}
+
+// Fortran Fw.d edit descriptor: right-justified, asterisks when the value does not fit; d = 0 keeps the decimal point
+inline std::string fortran_f(double x, int w, int d)
+{
+    char b[64];
+    if (std::isnan(x)) snprintf(b, sizeof b, "%*s", w, "NaN");
+    else if (std::isinf(x)) snprintf(b, sizeof b, "%*s", w, x > 0 ? "Infinity" : "-Infinity");
+    else if (d == 0) snprintf(b, sizeof b, "%*.0f.", w - 1, x);
+    else snprintf(b, sizeof b, "%*.*f", w, d, x);
+    std::string r = b;
+    if ((int)r.size() > w) {   // gfortran drops the optional leading zero before giving up
+        const size_t z = r.find("0.");
+        if (z != std::string::npos && (z == 0 || r[z - 1] == '-' || r[z - 1] == ' ') && (int)r.size() == w + 1) r.erase(z, 1);
+    }
+    if ((int)r.size() > w) r.assign(w, '*');
+    return r;
+}
 
 // End of a command-line run, after the output files are closed: the process is about to exit, so the page-locked buffers
 // (cudaFreeHost of several GB costs ~0.1 s per GB) and the CUDA context are left to the operating system.  The device is
