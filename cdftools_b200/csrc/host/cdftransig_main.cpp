@@ -1,7 +1,8 @@
 // cdftransig_xy3d_gpu -- C++ twin of the cdftransig_xy3d command line (src/cdftransig_xy3d.f90) on top of libcdfgpu.
 // Same options (-c CONFIG-CASE -l tags... [-code code] [-S] [-depref] [-nbins] [-sigmin] [-sigzoom] [-full] [-v] [-vvl]
 // [-o] [-teos10]), the same DRAKKAR file sets (CONFCASE_TAG_gridU/V/T[/S].nc, modutils.f90:85-114), mesh files, output
-// variables (vouxysig, vovxysig on a sigma_N axis) and exit codes (99 usage / missing file, 98 NetCDF, 97 GPU library).
+// variables (vouxysig, vovxysig on a sigma_N axis) and exit codes (99 usage / missing file, 98 NetCDF, 97 GPU library); -nc4 is
+// accepted and writes classic NetCDF, as a reference build without key_netcdf4 does.
 // The reference nests levels outside tags and frames because it reads one level at a time (:370-463); with the
 // accumulators resident on the device a frame (all levels) is the unit here -- see INTEGRATION.md section 4c.
 #include <string.h>
@@ -58,7 +59,7 @@ int main(int argc, char **argv)
         else if (a == "-v") lprint = true;
         else if (a == "-vvl") lvvl = true;
         else if (a == "-o") cf_out = next();
-        else if (a == "-nc4") { printf(" ERROR : -nc4 : NetCDF-4 output is not available in the GPU twin (no HDF5 library).\n"); stop(99); }
+        else if (a == "-nc4") note_nc4();   // cdftransig_xy3d.f90:179
         else if (a == "-teos10") lteos10 = true;
         else { printf(" ERROR : %s : unkown option.\n", a.c_str()); stop(99); }
     }
