@@ -61,7 +61,7 @@ constexpr int kSigTabSlack = CDF_SIG_TAB_SLACK; // a new band starts this many b
 #define CDF_SIG_PREFETCH_VA 1   // V / area of window n+2 in flight during window n (0: only T / S of window n+1)
 #endif
 #ifndef CDF_SIG_SEG_WIN
-#define CDF_SIG_SEG_WIN 6
+#define CDF_SIG_SEG_WIN 16
 #endif
 constexpr int kSigSegWin = CDF_SIG_SEG_WIN;     // windows per run grabbed by a warp, at most
 static_assert(kSigTabRows == 8 || kSigTabRows == 16, "table reduce is written for 8 or 16 rows");
