@@ -224,12 +224,17 @@ class Reader {
         case NC_DOUBLE: for (uint64_t i = 0; i < nelem; ++i) out[i] = (float)((double *)buf)[i]; break;
         default: err = v.name + ": not a numeric variable"; return false;
         }
+        // Caution : order does matter (cdfio.F90:1599-1602): three separate passes, each one skipping the values that equal
+        // the missing value AT THAT POINT -- scaled values are compared again before the offset is added
         float sf = 1.f, ao = 0.f;
-        if (needs_unpack(v, &sf, &ao))
-            for (uint64_t i = 0; i < nelem; ++i) out[i] = out[i] * sf + ao;
-        if (const Att *a = v.att("savelog10"))
-            if (a->as_double() != 0.0)
-                for (uint64_t i = 0; i < nelem; ++i) out[i] = __builtin_powf(10.f, out[i]);
+        needs_unpack(v, &sf, &ao);
+        const float sp = spval(v);
+        if (sf != 1.f)
+            for (uint64_t i = 0; i < nelem; ++i) if (out[i] != sp) out[i] = out[i] * sf;
+        if (ao != 0.f)
+            for (uint64_t i = 0; i < nelem; ++i) if (out[i] != sp) { volatile float t = out[i] + ao; out[i] = t; }
+        if (has_log(v))
+            for (uint64_t i = 0; i < nelem; ++i) if (out[i] != sp) out[i] = __builtin_powf(10.f, out[i]);
         return true;
     }
     bool read_f64(const Var &v, long rec, uint64_t elem_off, uint64_t nelem, double *out)

@@ -34,6 +34,34 @@ def test_reader_parses_scipy_files(tools, tmp_path, version):
     assert d["vars"]["e3v_0"]["sum"] == pytest.approx(float(m.e3v_0.astype(np.float64).sum()), rel=1e-12)
 
 
+def test_reader_unpacks_like_getvar(tools, tmp_path):
+    """Packed variables (NC_SHORT + scale_factor / add_offset) and savelog10: getvar applies them in three passes and leaves
+    the values that equal the missing value alone (src/cdfio.F90:1599-1602)."""
+    from scipy.io import netcdf_file
+    f = netcdf_file(str(tmp_path / "packed.nc"), "w", version=2)
+    f.createDimension("x", 6)
+    raw = np.array([100, -200, 32767, 0, 15, 32767], np.int16)
+    v = f.createVariable("vpacked", "h", ("x",))
+    v[:] = raw
+    v.scale_factor = np.float32(0.01)
+    v.add_offset = np.float32(2.5)
+    v.missing_value = np.int16(32767)
+    w = f.createVariable("vlog", "f", ("x",))
+    w[:] = np.array([0.0, 1.0, -1.0, 9999.0, 2.0, 0.5], np.float32)
+    w.savelog10 = np.int32(1)
+    w.missing_value = np.float32(9999.0)
+    f.close()
+    d = json.loads(subprocess.run([tools["nc3dump"], tmp_path / "packed.nc"], capture_output=True, text=True, check=True).stdout)
+    x = raw.astype(np.float32)
+    keep = x == np.float32(32767.0)
+    x = np.where(keep, x, x * np.float32(0.01))
+    x = np.where(x == np.float32(32767.0), x, x + np.float32(2.5))
+    assert d["vars"]["vpacked"]["sum"] == pytest.approx(float(x.astype(np.float64).sum()), rel=1e-12)
+    assert d["vars"]["vpacked"]["spval"] == 32767.0
+    y = np.array([1.0, 10.0, 0.1, 9999.0, 100.0, 10 ** 0.5], np.float64)
+    assert d["vars"]["vlog"]["sum"] == pytest.approx(float(y.sum()), rel=1e-6)
+
+
 def test_reader_rejects_non_netcdf(tools, tmp_path):
     p = tmp_path / "x.nc"
     p.write_bytes(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
