@@ -104,13 +104,17 @@ int main(int argc, char **argv)
     const char *vn[6] = {"zomsfglo", "zomsfatl", "zomsfinp", "zomsfind", "zomsfpac", "zomsfinp0"};
     const char *vl[6] = {"Global", "Atlantic", "IndoPacif", "Indian", "pacif", "IndPac0"};
     const char *dsuf[3] = {"_sh", "_bt", "_ag"};
-    const char *dlong[3] = {"GeoShear_Merid_StreamFunction", "Barotropic_Merid_StreamFunction", "Ageostoph_Merid_StreamFunction"};
+    // long names as the reference spells them (cdfmoc.f90:1041-1176): "Ageostoph" for the global cell only, "_Pacif" in the
+    // components of the Pacific cell
+    const char *dlong[3] = {"GeoShear_Merid_StreamFunction", "Barotropic_Merid_StreamFunction", "Ageostroph_Merid_StreamFunction"};
+    const char *vld[6] = {"Global", "Atlantic", "IndoPacif", "Indian", "Pacif", "IndPac0"};
     std::vector<OutVar> ovars;
     for (int b = 0; b < (lbas ? 6 : 1); ++b) {
         ovars.push_back({vn[b], std::string("Meridional_Overt.Cell_") + vl[b], "Sverdrup", -1000.f, 1000.f});
         if (ldec)
             for (int d = 0; d < 3; ++d)
-                ovars.push_back({std::string(vn[b]) + dsuf[d], std::string(dlong[d]) + (b ? std::string("_") + vl[b] : ""),
+                ovars.push_back({std::string(vn[b]) + dsuf[d],
+                                 b ? std::string(dlong[d]) + "_" + vld[b] : std::string(d == 2 ? "Ageostoph_Merid_StreamFunction" : dlong[d]),
                                  "Sverdrup", -1000.f, 1000.f});
     }
     std::vector<double> tim(npt, 0.0);
